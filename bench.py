@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of compu-b200 (contract: see the task prompt; metric from BASELINE.json).
+
+Workload at N=1 (BASELINE.json configs[1]): batched inflate of 65,536 independent zlib streams of 64 KiB synthetic
+Markov text (compressed by madler zlib 1.3 at level 6, the "reference-encoded" input) on one B200. With N>1 each rank
+inflates its own 65,536-stream shard (weak scaling, no data-path collective: streams are independent).
+
+  value        uncompressed GB/s, inputs and outputs resident in HBM (CUDA events around K launches)
+  e2e          the same metric through the host-memory C-ABI call cz_inflate_batch: pinned host buffers, H2D of the
+               compressed streams and D2H of the decoded bytes inside the timed region
+  roofline     (U + C) bytes per launch / average launch time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline the oracle (compu's glue over zlib 1.3 — stand-in for compu zlib-ng + rayon) on the host cores
+
+`--impl reference` times that CPU path alone (all host threads) and prints the same JSON line with "impl": "reference".
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import zlib
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STREAM_BYTES = 65536
+METRIC = "inflate_uncompressed_GBps"
+UNIT = "GB/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=65536, help="streams per GPU (cfg2: 65536)")
+    ap.add_argument("--seed", type=int, default=20261018)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def _p(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def compress_streams(plain, n, threads):
+    """zlib 1.3 level 6, windowBits 15, one independent stream per 64 KiB (what compu's Encoder would emit per item)."""
+    mv = memoryview(plain)
+
+    def work(rng):
+        return [zlib.compress(mv[i * STREAM_BYTES:(i + 1) * STREAM_BYTES], 6) for i in rng]
+
+    step = max(1, n // (threads * 8))
+    ranges = [range(i, min(n, i + step)) for i in range(0, n, step)]
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        parts = list(ex.map(work, ranges))
+    streams = [s for p in parts for s in p]
+    return streams
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index),
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for k, nme in enumerate(names):
+                if f[3 + k].lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_inflate_leg(streams_sample, threads, repeats=3):
+    """Oracle on the host cores (the ONLY place bench.py executes oracle/). Returns (GB/s uncompressed, seconds)."""
+    import oracle
+    L = oracle.lib()
+    n = len(streams_sample)
+    offs = np.zeros(n + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(s) for s in streams_sample], dtype=np.uint64)
+    inbuf = np.frombuffer(b"".join(streams_sample) + b"\0" * 16, dtype=np.uint8)
+    out_off = (np.arange(n + 1, dtype=np.uint64) * STREAM_BYTES)
+    out = np.empty(n * STREAM_BYTES + 16, dtype=np.uint8)
+    lens = np.zeros(n, dtype=np.uint64)
+    st = np.zeros(n, dtype=np.int32)
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        bad = L.oz_inflate_batch(n, _p(inbuf), _p(offs), _p(out), _p(out_off), _p(lens), _p(st), 15, threads)
+        dt = time.perf_counter() - t0
+        assert bad == 0
+        best = dt if best is None or dt < best else best
+    return n * STREAM_BYTES / best / 1e9, best
+
+
+def host_synth(n, seed):
+    """Same bytes as the device generator (cz_synth_fill_host), for the --impl reference arm when no GPU work is wanted."""
+    from compu_b200 import _lib
+    L = _lib.lib()
+    corpus = np.frombuffer(open(os.path.join(ROOT, "tests", "golden", "alice29.txt"), "rb").read(), dtype=np.uint8)
+    model = np.zeros(int(L.cz_synth_model_bytes()), dtype=np.uint8)
+    _lib.check(L.cz_synth_build_model(_p(corpus), len(corpus), _p(model)), "cz_synth_build_model")
+    offs = np.arange(n + 1, dtype=np.uint64) * STREAM_BYTES
+    out = np.empty(n * STREAM_BYTES, dtype=np.uint8)
+    _lib.check(L.cz_synth_fill_host(0, seed, n, _p(out), _p(offs), _p(model)), "cz_synth_fill_host")
+    return out, model
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path for this metric (oracle port over zlib 1.3, all host threads)."""
+    if rank != 0:
+        return
+    import oracle
+    threads = oracle.lib().oz_max_threads()
+    # bounded sample of the same workload: enough streams for ~1 s per step on this host
+    n = min(args.streams, max(256, 512 * threads))
+    plain, _ = host_synth(n, args.seed)
+    streams = compress_streams(plain, n, threads)
+    for _ in range(args.warmup):
+        cpu_inflate_leg(streams, threads, repeats=1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_inflate_leg(streams, threads, repeats=1)
+    dt = time.perf_counter() - t0
+    val = args.steps * n * STREAM_BYTES / dt / 1e9
+    sample = "%d of %d streams x 64 KiB per step (same generator, same seed)" % (n, args.streams)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "cfg2: batched inflate of independent 64 KiB zlib streams (Markov text, zlib 1.3 L6)",
+                   "streams_per_step": n, "stream_bytes": STREAM_BYTES, "window_bits": 15,
+                   "codec": "compu glue restated in C over madler zlib 1.3 (stand-in for compu zlib-ng + rayon)"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from compu_b200 import _lib
+
+    L = _lib.lib()
+    _lib.require_device()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.streams
+    U = n * STREAM_BYTES
+    seed = args.seed + rank * n  # every rank inflates different streams
+    stream = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+
+    # ---- synthetic plaintext on the device (Markov text from the alice29 model), then reference-encode on the host
+    corpus = np.frombuffer(open(os.path.join(ROOT, "tests", "golden", "alice29.txt"), "rb").read(), dtype=np.uint8)
+    model = np.zeros(int(L.cz_synth_model_bytes()), dtype=np.uint8)
+    _lib.check(L.cz_synth_build_model(_p(corpus), len(corpus), _p(model)), "cz_synth_build_model")
+    d_model = torch.from_numpy(model).to(dev)
+    d_plain = torch.empty(U, dtype=torch.uint8, device=dev)
+    d_out_off = (torch.arange(n + 1, dtype=torch.int64, device=dev) * STREAM_BYTES)
+    t0 = time.perf_counter()
+    _lib.check(L.cz_synth_fill_device(sp, 0, seed, n, d_plain.data_ptr(), d_out_off.data_ptr(), d_model.data_ptr()), "synth")
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t0
+    plain = d_plain.cpu().numpy()
+    threads = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    streams = compress_streams(plain, n, max(1, threads // max(1, world)))
+    t_comp = time.perf_counter() - t0
+    C = sum(len(s) for s in streams)
+    in_off = np.zeros(n + 1, dtype=np.int64)
+    in_off[1:] = np.cumsum([len(s) for s in streams])
+
+    # pinned host buffers (the pinned-buffer management of the boundary: cz_host_alloc)
+    h_in_p = L.cz_host_alloc(C + 16)
+    h_out_p = L.cz_host_alloc(U + 16)
+    assert h_in_p and h_out_p, _lib.last_error()
+    h_in = np.ctypeslib.as_array(ctypes.cast(h_in_p, ctypes.POINTER(ctypes.c_uint8)), shape=(C + 16,))
+    h_out = np.ctypeslib.as_array(ctypes.cast(h_out_p, ctypes.POINTER(ctypes.c_uint8)), shape=(U + 16,))
+    pos = 0
+    for s in streams:
+        h_in[pos:pos + len(s)] = np.frombuffer(s, dtype=np.uint8)
+        pos += len(s)
+
+    d_in = torch.from_numpy(h_in).to(dev)
+    d_in_off = torch.from_numpy(in_off).to(dev)
+    d_out = torch.empty(U + 16, dtype=torch.uint8, device=dev)
+    d_lens = torch.zeros(n, dtype=torch.int64, device=dev)
+    d_stat = torch.zeros(n, dtype=torch.int32, device=dev)
+    ws_bytes = int(L.cz_inflate_workspace_bytes(n))
+    d_ws = torch.zeros(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+
+    def step():
+        rc = L.cz_inflate_batch_device(sp, n, d_in.data_ptr(), d_in_off.data_ptr(), d_out.data_ptr(), d_out_off.data_ptr(),
+                                       d_lens.data_ptr(), d_stat.data_ptr(), None, 15, d_ws.data_ptr(), d_ws.numel())
+        _lib.check(rc, "cz_inflate_batch_device")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- correctness gate before any timing: every stream Finished and bytes identical to the plaintext
+    step()
+    torch.cuda.synchronize()
+    assert bool((d_stat == 2).all()), "not every stream finished: %s" % torch.unique(d_stat).tolist()
+    assert bool((d_lens == STREAM_BYTES).all())
+    assert torch.equal(d_out[:U], d_plain), "inflated bytes differ from the plaintext"
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_step = ms / args.steps
+    value = world * U / (ms_step * 1e-3) / 1e9
+
+    # ---- end to end through the host-memory C ABI (pinned host buffers, H2D + D2H inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        h_in_off = in_off.astype(np.uint64)
+        h_out_off = (np.arange(n + 1, dtype=np.uint64) * STREAM_BYTES)
+        h_lens = np.zeros(n, dtype=np.uint64)
+        h_stat = np.zeros(n, dtype=np.int32)
+
+        def e2e_step():
+            rc = L.cz_inflate_batch(n, ctypes.c_void_p(h_in_p), _p(h_in_off), ctypes.c_void_p(h_out_p), _p(h_out_off), _p(h_lens),
+                                    _p(h_stat), None, 15, 1 << local_rank)
+            _lib.check(rc, "cz_inflate_batch")
+
+        for _ in range(max(1, min(args.warmup, 2))):
+            e2e_step()
+        assert (h_stat == 2).all()
+        k = np.random.default_rng(1).integers(0, n, 64)
+        for i in k:
+            assert (h_out[i * STREAM_BYTES:(i + 1) * STREAM_BYTES] == plain[i * STREAM_BYTES:(i + 1) * STREAM_BYTES]).all()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * U * args.steps / dt / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": int(C + 16 * (n + 1)), "d2h_bytes_per_step": int(U + 12 * n),
+               "ms_per_step": dt / args.steps * 1e3}
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        achieved = (U + C) / (ms_step * 1e-3) / 1e9
+        cpu = None
+        if not args.no_cpu and world == 1:
+            import oracle
+            cthreads = oracle.lib().oz_max_threads()
+            ns = min(n, max(256, 512 * cthreads))
+            v, secs = cpu_inflate_leg(streams[:ns], cthreads)
+            cpu = {"value": v, "unit": UNIT, "cores": cthreads, "kind": "port",
+                   "sample": "first %d of %d streams, best of 3 (%.2f s each); zlib 1.3 stands in for zlib-ng" % (ns, n, secs)}
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get("inflate_cfg2_dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": "cfg2: batched inflate of 65,536 independent 64 KiB zlib streams (Markov text, zlib 1.3 L6)",
+                       "streams_per_gpu": n, "stream_bytes": STREAM_BYTES, "window_bits": 15, "ratio": U / C,
+                       "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no flush needed" % ((U + C) / 1e9),
+                       "inflate_cfg": os.environ.get("CZ_INFLATE_CFG", "default"),
+                       "setup_s": {"synth_gpu": round(t_gen, 3), "zlib_compress_host": round(t_comp, 2)}},
+            "e2e": e2e,
+            "gpu_launches": args.steps,  # one inflate kernel per step (plus a 256-byte memset node for the work counter)
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": int(U + C)},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    L.cz_host_free(ctypes.c_void_p(h_in_p))
+    L.cz_host_free(ctypes.c_void_p(h_out_p))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

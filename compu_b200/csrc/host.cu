@@ -1,0 +1,386 @@
+// host.cu — host side of the C ABI: device contexts, pinned/device buffer management, the batched host-memory entry
+// points and the streaming Decoder that maps compu's chunked contract onto one-shot GPU kernels.
+//
+// Reference contract followed here (file:line under /root/reference):
+//   cz_decode status map / remainders  src/decoder/mod.rs:459-486 (internal_zlib_impl_decode!)
+//   reset returns the instance to use  src/decoder/mod.rs:433-441, src/decoder/zlib_ng.rs:99-108
+//   describe_error static text         src/decoder/zlib_ng.rs:118-123 (zError), src/utils.rs:4-13
+//   compu_malloc/compu_free            src/mem.rs:27-49 (here: page-locked variants for DMA)
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
+#include "host_common.h"
+
+namespace czh {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+bool cuda_ok(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return false;
+}
+
+static std::mutex g_ctx_mu;
+static DeviceCtx g_ctx[64];
+static int g_ndev = -1;
+
+static int probe_devices() {
+    if (g_ndev >= 0) return g_ndev;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    if (n > 64) n = 64;
+    g_ndev = n;
+    return n;
+}
+
+DeviceCtx *device_ctx(int dev) {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    int n = probe_devices();
+    if (dev < 0 || dev >= n) { set_error("no CUDA device %d (found %d)", dev, n); return nullptr; }
+    DeviceCtx &c = g_ctx[dev];
+    if (c.dev == dev) return c.ok ? &c : nullptr;
+    c.dev = dev;
+    cudaDeviceProp prop;
+    if (!CZ_CUDA(cudaGetDeviceProperties(&prop, dev))) return nullptr;
+    if (prop.major != 10) {  // the only code in this library is sm_100a SASS
+        set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+        return nullptr;
+    }
+    c.sm_count = prop.multiProcessorCount;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    if (!CZ_CUDA(cudaSetDevice(dev))) return nullptr;
+    czk::CrcTables t;
+    czk::init_crc_tables(&t);
+    bool ok = CZ_CUDA(cudaMalloc(&c.d_crc, sizeof t)) && CZ_CUDA(cudaMemcpy(c.d_crc, &t, sizeof t, cudaMemcpyHostToDevice));
+    cudaSetDevice(prev);
+    c.ok = ok;
+    return ok ? &c : nullptr;
+}
+
+int usable_device_count() {
+    int n;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        n = probe_devices();
+    }
+    int k = 0;
+    for (int d = 0; d < n; d++)
+        if (device_ctx(d)) k++;
+    return k;
+}
+
+bool DevBuf::reserve(size_t bytes) {
+    if (bytes <= cap) return true;
+    release();
+    size_t want = align_up(bytes + bytes / 8 + 256, 256);
+    if (!CZ_CUDA(cudaMalloc(&p, want))) { p = nullptr; return false; }
+    cap = want;
+    return true;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+}
+bool PinBuf::reserve(size_t bytes, bool keep, size_t keep_bytes) {
+    if (bytes <= cap) return true;
+    size_t want = align_up(bytes + bytes / 2 + 4096, 4096);
+    void *np = nullptr;
+    if (!CZ_CUDA(cudaHostAlloc(&np, want, cudaHostAllocDefault))) return false;
+    if (keep && p && keep_bytes) memcpy(np, p, keep_bytes);
+    if (p) cudaFreeHost(p);
+    p = np;
+    cap = want;
+    return true;
+}
+void PinBuf::release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// One device's share of a batched inflate: H2D, kernel, D2H on its own stream. Buffers are cached per thread+device.
+struct InflateWork {
+    DevBuf in, out, meta;
+    cudaStream_t stream = nullptr;
+    int dev = -1;
+    bool init(int d) {
+        if (dev == d && stream) return true;
+        dev = d;
+        return CZ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    }
+    ~InflateWork() {
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static inline uint32_t first_device(uint32_t mask) { return mask ? (uint32_t)__builtin_ctz(mask) : 0; }
+
+// Inflate units [u0,u1) of a packed host batch on device `dev`. Offsets are rebased so that the device buffers only
+// hold this shard. Synchronous from the caller's point of view (returns after the D2H copies have landed).
+static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const uint8_t *in, const uint64_t *in_off, uint8_t *out,
+                         const uint64_t *out_off, uint64_t *out_lens, int32_t *statuses, uint64_t *in_consumed,
+                         int window_bits, int segment_mode, uint32_t *checks) {
+    DeviceCtx *ctx = device_ctx(dev);
+    if (!ctx) return CZ_E_NO_DEVICE;
+    if (!CZ_CUDA(cudaSetDevice(dev)) || !w.init(dev)) return CZ_E_MEM;
+    const size_t n = u1 - u0;
+    if (!n) return 0;
+    const uint64_t ib = in_off[u0], ie = in_off[u1], ob = out_off[u0], oe = out_off[u1];
+    // meta layout: in_off[n+1] out_off[n+1] out_lens[n] consumed[n] statuses[n] checks[2n] workspace[256]
+    const size_t m_inoff = 0, m_outoff = m_inoff + 8 * (n + 1), m_lens = m_outoff + 8 * (n + 1), m_cons = m_lens + 8 * n,
+                 m_stat = m_cons + 8 * n, m_chk = align_up(m_stat + 4 * n, 8), m_ws = align_up(m_chk + 8 * n, 256),
+                 m_total = m_ws + 256;
+    if (!w.in.reserve(ie - ib + 16) || !w.out.reserve(oe - ob + 16) || !w.meta.reserve(m_total)) return CZ_E_MEM;
+    std::vector<uint64_t> offs(2 * (n + 1));
+    for (size_t i = 0; i <= n; i++) { offs[i] = in_off[u0 + i] - ib; offs[n + 1 + i] = out_off[u0 + i] - ob; }
+    uint8_t *dm = w.meta.as<uint8_t>();
+    cudaStream_t st = w.stream;
+    if (!CZ_CUDA(cudaMemcpyAsync(dm, offs.data(), 16 * (n + 1), cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
+    if (ie > ib && !CZ_CUDA(cudaMemcpyAsync(w.in.p, in + ib, ie - ib, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
+    int r = launch_inflate(st, ctx, n, w.in.as<uint8_t>(), (const uint64_t *)(dm + m_inoff), w.out.as<uint8_t>(),
+                           (const uint64_t *)(dm + m_outoff), (uint64_t *)(dm + m_lens), (int32_t *)(dm + m_stat),
+                           (uint64_t *)(dm + m_cons), checks ? (uint32_t *)(dm + m_chk) : nullptr, window_bits, segment_mode,
+                           checks ? 3 : 0, dm + m_ws, 256);
+    if (r) return r;
+    if (oe > ob && !CZ_CUDA(cudaMemcpyAsync(out + ob, w.out.p, oe - ob, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+    if (!CZ_CUDA(cudaMemcpyAsync(out_lens + u0, dm + m_lens, 8 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+    if (!CZ_CUDA(cudaMemcpyAsync(statuses + u0, dm + m_stat, 4 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+    if (in_consumed && !CZ_CUDA(cudaMemcpyAsync(in_consumed + u0, dm + m_cons, 8 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+    if (checks && !CZ_CUDA(cudaMemcpyAsync(checks + 2 * u0, dm + m_chk, 8 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+    return 0;
+}
+
+// Contiguous shards balanced by compressed bytes (contiguous per GPU keeps H2D one large copy).
+static void split_by_bytes(size_t n, const uint64_t *off, int parts, std::vector<size_t> &cuts) {
+    cuts.assign(parts + 1, n);
+    cuts[0] = 0;
+    const uint64_t total = off[n] - off[0];
+    size_t u = 0;
+    for (int p = 1; p < parts; p++) {
+        const uint64_t target = off[0] + total * p / parts;
+        while (u < n && off[u] < target) u++;
+        cuts[p] = u;
+    }
+    cuts[parts] = n;
+}
+
+int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint8_t *out, const uint64_t *out_off,
+                       uint64_t *out_lens, int32_t *statuses, uint64_t *in_consumed, int window_bits, int segment_mode,
+                       uint32_t *checks, uint32_t devices_mask) {
+    if (probe_devices() == 0) { set_error("no CUDA device"); return CZ_E_NO_DEVICE; }
+    if (!devices_mask) devices_mask = 1;
+    std::vector<int> devs;
+    for (int d = 0; d < 32; d++)
+        if (devices_mask >> d & 1) devs.push_back(d);
+    for (int d : devs)
+        if (!device_ctx(d)) return CZ_E_NO_DEVICE;
+    static thread_local InflateWork works[32];
+    int prev = 0;
+    cudaGetDevice(&prev);
+    std::vector<size_t> cuts;
+    split_by_bytes(n, in_off, (int)devs.size(), cuts);
+    int rc = 0;
+    // enqueue every shard first (copies and kernels of different devices overlap), then wait for all
+    for (size_t k = 0; k < devs.size() && !rc; k++)
+        rc = inflate_shard(works[devs[k]], devs[k], cuts[k], cuts[k + 1], in, in_off, out, out_off, out_lens, statuses,
+                           in_consumed, window_bits, segment_mode, checks);
+    for (size_t k = 0; k < devs.size(); k++) {
+        if (!works[devs[k]].stream) continue;
+        cudaSetDevice(devs[k]);
+        if (!CZ_CUDA(cudaStreamSynchronize(works[devs[k]].stream)) && !rc) rc = CZ_E_MEM;
+    }
+    cudaSetDevice(prev);
+    return rc;
+}
+
+}  // namespace czh
+
+using namespace czh;
+
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" int cz_device_count(void) { return usable_device_count(); }
+extern "C" const char *cz_version(void) { return "compu-b200 0.1 (sm_100a)"; }
+extern "C" const char *cz_last_error(void) { return g_err; }
+
+extern "C" void *cz_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (probe_devices() == 0) { set_error("no CUDA device"); return nullptr; }
+    if (!CZ_CUDA(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable))) return nullptr;
+    return p;
+}
+extern "C" void cz_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+extern "C" const char *cz_describe_error(int32_t code) {
+    // same table as zError (zlib z_errmsg[]), so describe_error() parity holds for every code the backend returns
+    switch (code) {
+        case 2: return "need dictionary";
+        case 1: return "stream end";
+        case 0: return "";
+        case -1: return "file error";
+        case -2: return "stream error";
+        case -3: return "data error";
+        case -4: return "insufficient memory";
+        case -5: return "buffer error";
+        case -6: return "incompatible version";
+        default: return "";
+    }
+}
+
+extern "C" uint32_t cz_adler32_combine(uint32_t a, uint32_t b, uint64_t len2) { return czk::adler32_combine_u(a, b, len2); }
+extern "C" uint32_t cz_crc32_combine(uint32_t a, uint32_t b, uint64_t len2) { return czk::crc32_combine_u(a, b, len2); }
+
+extern "C" int cz_inflate_batch(size_t n, const uint8_t *in, const uint64_t *in_offsets, uint8_t *out,
+                                const uint64_t *out_offsets, uint64_t *out_lens, int32_t *statuses, uint64_t *in_consumed,
+                                int window_bits, uint32_t devices_mask) {
+    return inflate_batch_host(n, in, in_offsets, out, out_offsets, out_lens, statuses, in_consumed, window_bits, 0, nullptr,
+                              devices_mask);
+}
+
+extern "C" int cz_inflate_batch_ptrs(size_t n, const uint8_t *const *in_ptrs, const size_t *in_lens, uint8_t *const *out_ptrs,
+                                     const size_t *out_caps, size_t *out_lens, int32_t *statuses, int window_bits,
+                                     uint32_t devices_mask) {
+    // gather into the packed form (pinned), run, scatter
+    std::vector<uint64_t> ioff(n + 1, 0), ooff(n + 1, 0), lens(n, 0);
+    for (size_t i = 0; i < n; i++) { ioff[i + 1] = ioff[i] + in_lens[i]; ooff[i + 1] = ooff[i] + out_caps[i]; }
+    static thread_local PinBuf pin_in, pin_out;
+    if (!pin_in.reserve(ioff[n] + 16) || !pin_out.reserve(ooff[n] + 16)) return CZ_E_MEM;
+    for (size_t i = 0; i < n; i++) memcpy(pin_in.as<uint8_t>() + ioff[i], in_ptrs[i], in_lens[i]);
+    int rc = inflate_batch_host(n, pin_in.as<uint8_t>(), ioff.data(), pin_out.as<uint8_t>(), ooff.data(), lens.data(), statuses,
+                                nullptr, window_bits, 0, nullptr, devices_mask);
+    if (rc) return rc;
+    for (size_t i = 0; i < n; i++) {
+        memcpy(out_ptrs[i], pin_out.as<uint8_t>() + ooff[i], (size_t)lens[i]);
+        out_lens[i] = (size_t)lens[i];
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Streaming decoder. The GPU kernel is one-shot per stream, the contract is chunked in both directions
+// (tests/decoder.rs:34 hands a 1-byte output; tests/encoder.rs:149 feeds the input in 4 chunks). So the backend stages:
+// every byte of input is copied into a pinned staging buffer (the caller's slice is only borrowed for the call), the
+// stream staged so far is inflated on the device, the decoded prefix is held and drained over this and later calls.
+// Statuses follow the reference map: all input taken and stream not ended -> NeedInput; undelivered output ->
+// NeedOutput with output_remain == 0; stream end decoded and everything delivered -> Finished, with the bytes after
+// the end of the stream reported as input_remain.
+struct DecoderState {
+    int window_bits;
+    int dev;
+    PinBuf in;            // staged compressed bytes
+    size_t in_len = 0;
+    PinBuf out;           // decoded bytes (prefix of the stream's output)
+    size_t out_len = 0;   // valid bytes in `out`
+    size_t delivered = 0; // bytes already handed to the caller
+    size_t out_cap_hint = 0;
+    bool dirty = false;   // new input since the last device pass
+    bool done = false;    // stream end decoded
+    int32_t error = 0;    // sticky error code (<0, or 3 = need dictionary)
+    size_t stream_bytes = 0;  // compressed length of the stream once done
+};
+
+extern "C" void *cz_decoder_new(int window_bits) {
+    if (!(window_bits == -15 || window_bits == 15 || window_bits == 31 || window_bits == 47)) {
+        set_error("unsupported window_bits %d", window_bits);
+        return nullptr;
+    }
+    int dev = 0;
+    if (probe_devices() == 0 || !device_ctx(dev)) {
+        if (!g_err[0]) set_error("no usable sm_100 CUDA device");
+        return nullptr;  // => Interface::zlib_cuda(mode) returns None; there is no CPU path
+    }
+    DecoderState *s = new (std::nothrow) DecoderState();
+    if (!s) return nullptr;
+    s->window_bits = window_bits;
+    s->dev = dev;
+    return s;
+}
+
+extern "C" void *cz_decoder_reset(void *state) {
+    DecoderState *s = (DecoderState *)state;
+    if (!s) return nullptr;
+    s->in_len = s->out_len = s->delivered = 0;  // keeps the pinned allocations (cheap reset)
+    s->dirty = s->done = false;
+    s->error = 0;
+    s->stream_bytes = 0;
+    return s;
+}
+
+extern "C" void cz_decoder_free(void *state) { delete (DecoderState *)state; }
+
+static int decoder_pass(DecoderState *s) {
+    // inflate everything staged so far as one unit; grow the output buffer until the slot is large enough
+    size_t cap = std::max<size_t>(s->out_cap_hint, std::max<size_t>(s->in_len * 4, 1 << 16));
+    if (s->window_bits > 15 && s->in_len >= 18) {
+        // gzip ISIZE (mod 2^32) is a cheap hint when the whole member is present
+        const uint8_t *t = s->in.as<uint8_t>() + s->in_len - 4;
+        size_t isz = (size_t)t[0] | (size_t)t[1] << 8 | (size_t)t[2] << 16 | (size_t)t[3] << 24;
+        if (isz > cap && isz < ((size_t)1 << 31)) cap = isz;
+    }
+    for (;;) {
+        if (!s->out.reserve(cap + 16)) return CZ_E_MEM;
+        uint64_t in_off[2] = {0, s->in_len}, out_off[2] = {0, cap}, out_len = 0, consumed = 0;
+        int32_t status = 0;
+        int rc = inflate_batch_host(1, s->in.as<uint8_t>(), in_off, s->out.as<uint8_t>(), out_off, &out_len, &status, &consumed,
+                                    s->window_bits, 0, nullptr, 1u << s->dev);
+        if (rc) return rc;
+        if (status == CZ_DECODE_NEED_OUTPUT) { cap *= 2; continue; }
+        s->out_len = (size_t)out_len;
+        s->out_cap_hint = cap;
+        if (status == CZ_DECODE_FINISHED) { s->done = true; s->stream_bytes = (size_t)consumed; }
+        else if (status != CZ_DECODE_NEED_INPUT) s->error = status;
+        return 0;
+    }
+}
+
+extern "C" cz_result cz_decode(void *state, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len) {
+    DecoderState *s = (DecoderState *)state;
+    cz_result r;
+    r.input_remain = in_len;
+    r.output_remain = out_len;
+    if (!s) { r.status = CZ_E_STREAM; return r; }
+    if (s->error) { r.status = s->error == 3 ? 3 : s->error; return r; }
+    if (!s->done && in_len) {
+        if (!s->in.reserve(s->in_len + in_len + 16, true, s->in_len)) { r.status = CZ_E_MEM; return r; }
+        memcpy(s->in.as<uint8_t>() + s->in_len, in, in_len);
+        s->in_len += in_len;
+        s->dirty = true;
+        r.input_remain = 0;
+    }
+    if (s->dirty) {
+        s->dirty = false;
+        int rc = decoder_pass(s);
+        if (rc) { s->error = rc; r.status = rc; return r; }
+        if (s->done) {
+            // bytes staged beyond the end of the stream belong to the caller: they all come from this call
+            size_t extra = s->in_len - s->stream_bytes;
+            r.input_remain = extra <= in_len ? extra : in_len;
+            s->in_len = s->stream_bytes;
+        }
+    }
+    size_t avail = s->out_len - s->delivered;
+    size_t k = avail < out_len ? avail : out_len;
+    if (k) memcpy(out, s->out.as<uint8_t>() + s->delivered, k);
+    s->delivered += k;
+    r.output_remain = out_len - k;
+    if (s->delivered < s->out_len) r.status = CZ_DECODE_NEED_OUTPUT;
+    else if (s->error) r.status = s->error;  // everything decoded before the error has been delivered
+    else if (s->done) r.status = CZ_DECODE_FINISHED;
+    else if (in_len == 0 && k == 0) r.status = CZ_DECODE_NEED_OUTPUT;  // no progress possible: zlib's Z_BUF_ERROR -> NeedOutput (mod.rs:481)
+    else r.status = CZ_DECODE_NEED_INPUT;
+    return r;
+}

@@ -1,0 +1,58 @@
+// host_common.h — host-side plumbing shared by the C-ABI translation units (device contexts, buffers, errors).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/compu_b200.h"
+#include "czk_common.cuh"
+
+namespace czh {
+
+void set_error(const char *fmt, ...);
+bool cuda_ok(cudaError_t e, const char *what);
+#define CZ_CUDA(call) ::czh::cuda_ok((call), #call)
+
+// One per CUDA device, created lazily. Holds what kernels need that is device-resident and read-only.
+struct DeviceCtx {
+    int dev = -1;
+    int sm_count = 0;
+    czk::CrcTables *d_crc = nullptr;
+    bool ok = false;
+};
+DeviceCtx *device_ctx(int dev);  // nullptr if the device is unusable (not sm_100, CUDA failure)
+int usable_device_count();
+
+// Grow-only device / pinned-host buffers reused across calls (reset() keeps the allocation).
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t bytes);
+    void release();
+    ~DevBuf() { release(); }
+    template <class T>
+    T *as() { return (T *)p; }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool reserve(size_t bytes, bool keep = false, size_t keep_bytes = 0);
+    void release();
+    ~PinBuf() { release(); }
+    template <class T>
+    T *as() { return (T *)p; }
+};
+
+inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// kernel launchers (defined in inflate.cu / deflate.cu)
+int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out,
+                   const uint64_t *d_out_off, uint64_t *d_out_lens, int32_t *d_statuses, uint64_t *d_in_consumed,
+                   uint32_t *d_checks, int window_bits, int segment_mode, int check_kind, void *d_ws, uint64_t ws_bytes);
+
+}  // namespace czh

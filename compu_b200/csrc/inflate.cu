@@ -1,0 +1,107 @@
+// inflate.cu — instantiates the inflate kernel for sm_100a and exposes the device-memory C ABI
+// (cz_inflate_batch_device / cz_inflate_segments_device, include/compu_b200.h).
+#include <stdlib.h>
+
+#include "host_common.h"
+#include "inflate_kernel.cuh"
+
+namespace czh {
+
+struct InflateCfg {
+    int D, W;
+};
+
+template <int D, int W>
+static int launch_cfg(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams &P) {
+    auto kern = czk::inflate_kernel<D, W>;
+    const size_t smem = czk::inflate_smem_bytes<D, W>();
+    static bool configured[64] = {};
+    if (!configured[ctx->dev & 63]) {
+        if (!CZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return CZ_E_MEM;
+        configured[ctx->dev & 63] = true;
+    }
+    int per_sm = 0;
+    if (!CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, smem))) return CZ_E_MEM;
+    if (per_sm < 1) { set_error("inflate kernel <%d,%d> does not fit on an SM", D, W); return CZ_E_MEM; }
+    // persistent warps: one resident wave; slots pull units from the global counter
+    uint64_t slots_needed = (P.n + D - 1) / D;               // warps
+    uint64_t ctas_needed = (slots_needed + W - 1) / W;
+    uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
+    if (ctas_needed < grid) grid = ctas_needed;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, W * 32, smem, st>>>(P);
+    return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
+}
+
+static InflateCfg g_cfg = {0, 0};
+
+static InflateCfg pick_cfg() {
+    if (g_cfg.D == 0) {
+        InflateCfg c{8, 7};
+        if (const char *e = getenv("CZ_INFLATE_CFG")) {
+            int d = 0, w = 0;
+            if (sscanf(e, "%d,%d", &d, &w) == 2) { c.D = d; c.W = w; }
+        }
+        g_cfg = c;
+    }
+    return g_cfg;
+}
+
+int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out,
+                   const uint64_t *d_out_off, uint64_t *d_out_lens, int32_t *d_statuses, uint64_t *d_in_consumed,
+                   uint32_t *d_checks, int window_bits, int segment_mode, int check_kind, void *d_ws, uint64_t ws_bytes) {
+    if (n == 0) return 0;
+    if (n > 0xfffffff0u) { set_error("too many units in one launch"); return CZ_E_STREAM; }
+    if (ws_bytes < 256 || !d_ws) { set_error("inflate workspace too small"); return CZ_E_MEM; }
+    if (!(window_bits == -15 || window_bits == 15 || window_bits == 31 || window_bits == 47) && !segment_mode) {
+        set_error("unsupported window_bits %d", window_bits);
+        return CZ_E_STREAM;
+    }
+    czk::InflateParams P;
+    P.in = d_in; P.in_off = d_in_off; P.out = d_out; P.out_off = d_out_off; P.out_lens = d_out_lens; P.statuses = d_statuses;
+    P.in_consumed = d_in_consumed; P.checks = d_checks; P.counter = (unsigned long long *)d_ws; P.crc = ctx->d_crc;
+    P.n = (uint32_t)n; P.window_bits = window_bits; P.segment_mode = segment_mode; P.check_kind = check_kind;
+    if (!CZ_CUDA(cudaMemsetAsync(d_ws, 0, 256, st))) return CZ_E_MEM;
+    InflateCfg c = pick_cfg();
+#define CZ_CFG(d, w) if (c.D == d && c.W == w) return launch_cfg<d, w>(st, ctx, P)
+    CZ_CFG(1, 8); CZ_CFG(2, 8); CZ_CFG(4, 7); CZ_CFG(4, 4); CZ_CFG(8, 7); CZ_CFG(8, 4); CZ_CFG(8, 2); CZ_CFG(16, 3);
+    CZ_CFG(16, 1); CZ_CFG(32, 1);
+#undef CZ_CFG
+    set_error("CZ_INFLATE_CFG=%d,%d is not an instantiated configuration", c.D, c.W);
+    return CZ_E_STREAM;
+}
+
+}  // namespace czh
+
+using namespace czh;
+
+extern "C" uint64_t cz_inflate_workspace_bytes(size_t) { return 256; }
+
+extern "C" int cz_tune_inflate(int slots_per_warp, int warps_per_cta) {
+    g_cfg.D = slots_per_warp;
+    g_cfg.W = warps_per_cta;
+    return 0;
+}
+
+extern "C" int cz_inflate_batch_device(void *cuda_stream, size_t n, const uint8_t *d_in, const uint64_t *d_in_offsets,
+                                       uint8_t *d_out, const uint64_t *d_out_offsets, uint64_t *d_out_lens,
+                                       int32_t *d_statuses, uint64_t *d_in_consumed, int window_bits, void *d_workspace,
+                                       uint64_t workspace_bytes) {
+    int dev = 0;
+    if (!CZ_CUDA(cudaGetDevice(&dev))) return CZ_E_NO_DEVICE;
+    DeviceCtx *ctx = device_ctx(dev);
+    if (!ctx) return CZ_E_NO_DEVICE;
+    return launch_inflate((cudaStream_t)cuda_stream, ctx, n, d_in, d_in_offsets, d_out, d_out_offsets, d_out_lens, d_statuses,
+                          d_in_consumed, nullptr, window_bits, 0, 0, d_workspace, workspace_bytes);
+}
+
+extern "C" int cz_inflate_segments_device(void *cuda_stream, size_t n, const uint8_t *d_in, const uint64_t *d_in_offsets,
+                                          uint8_t *d_out, const uint64_t *d_out_offsets, uint64_t *d_out_lens,
+                                          int32_t *d_statuses, uint32_t *d_checks, void *d_workspace, uint64_t workspace_bytes) {
+    int dev = 0;
+    if (!CZ_CUDA(cudaGetDevice(&dev))) return CZ_E_NO_DEVICE;
+    DeviceCtx *ctx = device_ctx(dev);
+    if (!ctx) return CZ_E_NO_DEVICE;
+    return launch_inflate((cudaStream_t)cuda_stream, ctx, n, d_in, d_in_offsets, d_out, d_out_offsets, d_out_lens, d_statuses,
+                          nullptr, d_checks, -15, 1, d_checks ? 3 : 0, d_workspace, workspace_bytes);
+}

@@ -42,6 +42,7 @@ enum {
     CZ_DECODE_NEED_INPUT = 0,
     CZ_DECODE_NEED_OUTPUT = 1,
     CZ_DECODE_FINISHED = 2,
+    CZ_DECODE_NEED_DICT = 3, /* error: the adapter returns Err(DecodeError(2)) (zlib's Z_NEED_DICT; 2 is taken by Finished here) */
     CZ_E_STREAM = -2,         /* Z_STREAM_ERROR  */
     CZ_E_DATA = -3,           /* Z_DATA_ERROR    */
     CZ_E_MEM = -4,            /* Z_MEM_ERROR (also: CUDA failure / out of device memory) */
@@ -132,6 +133,10 @@ int cz_inflate_segmented(const uint8_t *in, uint64_t len, uint8_t *out, uint64_t
 /* ---------------------------------------------------------------- batched entry points (device memory) */
 /* Same contracts, all pointers are device pointers on the CURRENT CUDA device, work is enqueued on `cuda_stream`
    (a cudaStream_t passed as void*) and NOT synchronised. These are what bench.py times for the roofline figure. */
+
+/* Tuning knob: decoder slots per warp (streams decoded concurrently by one warp) and warps per CTA of the inflate kernel.
+   Only instantiated pairs are accepted at launch (see compu_b200/csrc/inflate.cu); default from CZ_INFLATE_CFG or 8,7. */
+int cz_tune_inflate(int slots_per_warp, int warps_per_cta);
 
 /* Scratch bytes cz_inflate_batch_device needs for n streams (0 is possible). */
 uint64_t cz_inflate_workspace_bytes(size_t n);

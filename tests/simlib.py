@@ -1,0 +1,48 @@
+"""ctypes access to the CPU-emulated kernels (tests/cusim) — test infrastructure only."""
+import ctypes, os, subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_DIR = os.path.join(_HERE, "cusim")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", _DIR, "-s"])
+        _lib = ctypes.CDLL(os.path.join(_DIR, "libcusim_kernels.so"))
+        _lib.sim_crc32_combine.restype = ctypes.c_uint32
+        _lib.sim_crc32_combine.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]
+        _lib.sim_adler32_combine.restype = ctypes.c_uint32
+        _lib.sim_adler32_combine.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint64]
+    return _lib
+
+
+def pack(chunks):
+    offs = np.zeros(len(chunks) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(c) for c in chunks])
+    buf = np.frombuffer(b"".join(chunks) + b"\0" * 8, dtype=np.uint8).copy()
+    return buf, offs
+
+
+def sim_inflate(streams, caps, window_bits, segment_mode=0, check_kind=0, D=4, grid=2, seed=1):
+    """Returns (outputs, statuses, out_lens, in_consumed, checks)."""
+    L = lib()
+    n = len(streams)
+    inbuf, in_off = pack(streams)
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    out_off[1:] = np.cumsum(caps)
+    out = np.full(int(out_off[-1]) + 64, 0xEE, dtype=np.uint8)
+    out_lens = np.zeros(n, dtype=np.uint64)
+    statuses = np.full(n, -99, dtype=np.int32)
+    consumed = np.zeros(n, dtype=np.uint64)
+    checks = np.zeros(2 * n, dtype=np.uint32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    r = L.sim_inflate(ctypes.c_size_t(n), p(inbuf), p(in_off), p(out), p(out_off), p(out_lens), p(statuses), p(consumed),
+                      p(checks), window_bits, segment_mode, check_kind, D, grid, ctypes.c_uint64(seed))
+    assert r == 0
+    outs = [bytes(out[int(out_off[i]):int(out_off[i]) + int(out_lens[i])]) for i in range(n)]
+    # nothing may be written past a slot's capacity
+    assert (out[int(out_off[-1]):] == 0xEE).all()
+    return outs, statuses, out_lens, consumed, checks

@@ -1,0 +1,129 @@
+"""GPU parity tests for inflate: the CUDA path through the C ABI vs the CPU oracle, on the reference's golden vectors,
+seeded synthetic inputs, and the domain's edge cases. Run with -m gpu on a B200."""
+import zlib
+
+import numpy as np
+import pytest
+
+import protocols
+from compu_b200 import _lib, batch
+from compu_b200.decoder import DecodeError, DecodeStatus, Interface, ZlibMode
+from helpers import assert_inflate_parity, fuzz_cases, oracle_inflate, zcomp
+
+pytestmark = pytest.mark.gpu
+
+
+def test_device_present():
+    assert _lib.require_device() >= 1
+
+
+@pytest.mark.parametrize("mode", [ZlibMode.Gzip, ZlibMode.Auto])
+def test_reference_decoder_protocol_on_golden_gzip(golden, mode):
+    # should_decode_zlib_ng_gzip (tests/decoder.rs:141-150) with the CUDA backend in place of zlib_ng
+    d = Interface.zlib_cuda(mode)
+    assert d is not None, _lib.last_error()
+    for data, comp in golden:
+        protocols.decoder_test_case(d, data, comp)
+
+
+def test_batch_golden_all_containers(golden):
+    for data, comp in golden:
+        outs, st, lens, cons = batch.inflate_batch([comp], [len(data)], 31)
+        assert st[0] == 2 and outs[0] == data and cons[0] == len(comp)
+        for wb in (15, -15, 31):
+            for lvl in (1, 6, 9):
+                s = zcomp(data, lvl, wb)
+                outs, st, _, cons = batch.inflate_batch([s, s + b"xyz"], [len(data), len(data)], wb)
+                assert list(st) == [2, 2] and outs[0] == data and outs[1] == data
+                assert list(cons) == [len(s), len(s)]
+
+
+@pytest.mark.parametrize("wbits", [15, 31, -15, 47])
+def test_fuzz_vs_oracle(alice, wbits):
+    datas, streams, caps = fuzz_cases(7000 + wbits, wbits, 400, alice)
+    ref_outs, ref_st, _ = oracle_inflate(streams, caps, wbits)
+    outs, st, lens, cons = batch.inflate_batch(streams, caps, wbits)
+    assert_inflate_parity(outs, st, ref_outs, ref_st, "wbits %d" % wbits)
+
+
+def test_many_64k_streams_vs_oracle(alice):
+    # cfg2 in miniature: independent 64 KiB zlib streams (text), level 6
+    rng = np.random.default_rng(5)
+    big = (alice * 8)
+    chunks = []
+    for i in range(512):
+        o = int(rng.integers(0, len(big) - 65536))
+        chunks.append(big[o:o + 65536])
+    streams = [zlib.compress(c, 6) for c in chunks]
+    outs, st, lens, cons = batch.inflate_batch(streams, [65536] * len(chunks), 15)
+    ref_outs, ref_st, _ = oracle_inflate(streams, [65536] * len(chunks), 15)
+    assert_inflate_parity(outs, st, ref_outs, ref_st)
+    assert (st == 2).all()
+
+
+def test_ragged_and_large_streams(alice):
+    # stream sizes 4 KiB .. 16 MiB (cfg5 shape), mixed classes
+    rng = np.random.default_rng(9)
+    datas = []
+    for sz in (4096, 5000, 70001, 1 << 20, (1 << 22) + 17, 1 << 24):
+        rep = (alice * (sz // len(alice) + 2))
+        a = np.frombuffer(rep[:sz], dtype=np.uint8).copy()
+        noise = rng.integers(0, 256, sz, dtype=np.uint8)
+        mask = rng.random(sz) < 0.02
+        a[mask] = noise[mask]
+        datas.append(a.tobytes())
+    datas.append(rng.integers(0, 256, 300000, dtype=np.uint8).tobytes())  # incompressible -> stored blocks
+    datas.append(b"")
+    streams = [zlib.compress(d, 6) for d in datas]
+    outs, st, lens, cons = batch.inflate_batch(streams, [len(d) for d in datas], 15)
+    assert (st == 2).all(), st
+    for o, d in zip(outs, datas):
+        assert o == d
+
+
+def test_error_codes_match_oracle(golden):
+    data, comp = golden[1]
+    d = Interface.zlib_cuda(ZlibMode.Gzip)
+    out = bytearray(len(data))
+    r = d.decode(comp[:len(comp) // 2], out)
+    assert r.status == DecodeStatus.NeedInput and r.input_remain == 0 and r.output_remain > 0
+    assert bytes(out[:len(out) - r.output_remain]) == data[:len(out) - r.output_remain]
+    r = d.decode(b"", out)  # zero-progress call
+    assert r.status == DecodeStatus.NeedOutput
+    d.reset()
+    bad = bytearray(comp)
+    bad[len(bad) // 2] ^= 0x40
+    r = d.decode(bytes(bad), out)
+    assert r.status == DecodeError(-3)
+    assert d.describe_error(r.status) == "data error"
+    d.reset()
+    bad = bytearray(comp)
+    bad[-6] ^= 1
+    r = d.decode(bytes(bad), out)
+    assert r.status == DecodeError(-3)
+    d.reset()
+    # trailing bytes after the stream end are handed back as input_remain
+    r = d.decode(comp + b"TRAIL", out)
+    assert r.status == DecodeStatus.Finished and r.input_remain == 5 and bytes(out) == data
+    # FDICT -> need dictionary (zlib code 2)
+    dz = Interface.zlib_cuda(ZlibMode.Zlib)
+    c = zlib.compressobj(6, zlib.DEFLATED, 15, 8, 0, b"some dictionary")
+    s = c.compress(b"hello hello") + c.flush()
+    r = dz.decode(s, out)
+    assert r.status == DecodeError(2)
+
+
+def test_inflate_config_sweep_is_consistent(alice):
+    # every instantiated (slots-per-warp, warps) configuration must give identical bytes
+    import os
+    import subprocess
+    import sys
+    code = ("import sys,zlib;sys.path.insert(0,'.');from compu_b200 import batch;"
+            "a=open('tests/golden/alice29.txt','rb').read();c=[a[i:i+30000] for i in range(0,len(a),30000)];"
+            "s=[zlib.compress(x,6) for x in c];o,st,_,_=batch.inflate_batch(s,[len(x) for x in c],15);"
+            "assert (st==2).all() and o==c;print('ok')")
+    for cfg in ("1,8", "2,8", "4,7", "8,7", "16,3", "32,1"):
+        env = dict(os.environ, CZ_INFLATE_CFG=cfg)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                           cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert r.returncode == 0 and "ok" in r.stdout, (cfg, r.stdout, r.stderr)
