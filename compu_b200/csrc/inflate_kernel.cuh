@@ -94,24 +94,26 @@ __host__ __device__ inline uint32_t dist_entry(uint32_t sym, uint32_t len) {
 }
 
 // Lane-local sequential bit reader over one compressed unit (LSB-first, RFC 1951 §3.1.1).
+// The position is not tracked per symbol: bits consumed = 32*widx - 8*mis - cnt, computed on demand. The next input
+// word is always prefetched into `nextw`, so the refill on the decode critical path is two ALU ops, not a load.
 struct BitReader {
     const uint32_t *words;  // 4-byte aligned base (<= first byte)
     uint32_t mis;           // first byte = (uint8_t*)words + mis
-    uint32_t widx, wend;    // next word to load / number of words that hold stream bytes
+    uint32_t widx, wend;    // words merged into buf so far / number of words that hold stream bytes
     uint32_t cnt;           // valid bits in buf
+    uint32_t nextw;         // words[widx], already loaded (0 past the end)
     uint64_t buf;
-    uint64_t consumed;      // bits consumed since the start of the unit
     uint64_t total;         // bits in the unit
 
+    __device__ __forceinline__ uint32_t load(uint32_t i) const { return i < wend ? __ldg(words + i) : 0u; }
     __device__ __forceinline__ void seek(uint64_t byte_pos) {
         uint64_t a = (uint64_t)mis + byte_pos;
-        widx = (uint32_t)(a >> 2);
+        uint32_t wi = (uint32_t)(a >> 2);
         uint32_t sh = (uint32_t)(a & 3) * 8;
-        uint32_t w = widx < wend ? __ldg(words + widx) : 0u;
-        buf = (uint64_t)(w >> sh);
+        buf = (uint64_t)(load(wi) >> sh);
         cnt = 32 - sh;
-        widx++;
-        consumed = byte_pos * 8;
+        widx = wi + 1;
+        nextw = load(widx);
     }
     __device__ __forceinline__ void init(const uint8_t *p, uint64_t len) {
         mis = (uint32_t)((uintptr_t)p & 3);
@@ -123,24 +125,25 @@ struct BitReader {
     // after refill(): cnt >= 33
     __device__ __forceinline__ void refill() {
         if (cnt <= 32) {
-            uint32_t w = widx < wend ? __ldg(words + widx) : 0u;
-            buf |= (uint64_t)w << cnt;
+            buf |= (uint64_t)nextw << cnt;
             cnt += 32;
             widx++;
+            nextw = load(widx);
         }
     }
     __device__ __forceinline__ uint32_t peek(uint32_t n) const { return (uint32_t)buf & ((1u << n) - 1u); }
     __device__ __forceinline__ void skip(uint32_t n) {
         buf >>= n;
         cnt -= n;
-        consumed += n;
     }
     __device__ __forceinline__ uint32_t get(uint32_t n) {  // n <= 16, caller guarantees cnt >= n
         uint32_t v = peek(n);
         skip(n);
         return v;
     }
-    __device__ __forceinline__ bool overrun() const { return consumed > total; }
+    __device__ __forceinline__ uint64_t consumed() const { return (uint64_t)widx * 32 - 8 * mis - cnt; }
+    // true when bits beyond the end of the unit have been consumed; cheap unless the reader is in the last words
+    __device__ __forceinline__ bool overrun() const { return widx >= wend && consumed() > total; }
     __device__ __forceinline__ uint32_t get_byte() {  // byte-wise header parsing
         refill();
         return get(8);
@@ -439,7 +442,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
 
     // ---- per-slot registers (meaningful on lanes < D)
     BitReader br;
-    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.consumed = 0; br.total = 0;
+    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.total = 0;
     int st = lane < D ? SS_IDLE : SS_EXIT;
     uint32_t unit = 0;
     const uint8_t *in_base = nullptr;
@@ -487,9 +490,9 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
 
         // ---- (3) block header
         if (st == SS_BLOCK) {
-            if (P.segment_mode && br.consumed >= br.total) {
+            if (P.segment_mode && br.consumed() >= br.total) {
                 // a full-flush segment ends byte-aligned exactly at the end of its input
-                result = br.consumed == br.total ? ST_FINISHED : ST_NEED_INPUT;
+                result = br.consumed() == br.total ? ST_FINISHED : ST_NEED_INPUT;
                 st = SS_TRAILER;
             } else {
                 br.refill();
@@ -497,7 +500,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 uint32_t btype = br.get(2);
                 if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; }
                 else if (btype == 0) {
-                    br.skip((uint32_t)((0 - br.consumed) & 7));
+                    br.skip((uint32_t)((0 - br.consumed()) & 7));
                     br.refill();
                     uint32_t len = br.get(16);
                     uint32_t nlen = br.get(16);
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                         break;
                     }
                     // invalid code; zero bits past a truncated input can land here too
-                    if (br.consumed + ((e & 15) ? (e & 15) : 1) > br.total) result = ST_NEED_INPUT; else result = ST_E_DATA;
+                    if (br.consumed() + ((e & 15) ? (e & 15) : 1) > br.total) result = ST_NEED_INPUT; else result = ST_E_DATA;
                     after_tokens = SS_FINISH;
                     break;
                 }
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 uint32_t de = my.dist_tab[br.peek(CZK_DIST_BITS)];
                 if (de & CZK_D_LONG) de = decode_long_dist(my, br.peek(15));
                 if (de & CZK_D_INVALID) {
-                    if (br.consumed + ((de & 15) ? (de & 15) : 1) > br.total) result = ST_NEED_INPUT; else result = ST_E_DATA;
+                    if (br.consumed() + ((de & 15) ? (de & 15) : 1) > br.total) result = ST_NEED_INPUT; else result = ST_E_DATA;
                     after_tokens = SS_FINISH;
                     break;
                 }
@@ -617,7 +620,8 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 if (badm) {
                     int fb = __ffs(badm) - 1;
                     total = __shfl_sync(CZK_FULL, pos, fb);  // keep everything before the bad token
-                    err = ST_E_DATA;
+                    // zlib looks at the output space before the distance (inflate.c MATCH: `if (left == 0) goto inf_leave`)
+                    err = opos + total >= ocap ? ST_NEED_OUTPUT : ST_E_DATA;
                 }
                 if (opos + total > ocap) {  // output slot full: deliver the prefix that fits
                     total = (uint32_t)(ocap - opos);
@@ -681,7 +685,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 uint8_t *ob = (uint8_t *)(uintptr_t)__shfl_sync(CZK_FULL, (unsigned long long)(uintptr_t)out_base, s);
                 const uint64_t opos = __shfl_sync(CZK_FULL, (unsigned long long)out_pos, s);
                 const uint64_t ocap = __shfl_sync(CZK_FULL, (unsigned long long)out_cap, s);
-                const uint64_t ipos = __shfl_sync(CZK_FULL, (unsigned long long)br.consumed, s) >> 3;
+                const uint64_t ipos = __shfl_sync(CZK_FULL, (unsigned long long)br.consumed(), s) >> 3;
                 const uint64_t ilen = __shfl_sync(CZK_FULL, (unsigned long long)in_len, s);
                 int err = -1;  // none
                 uint32_t n = len;
@@ -750,7 +754,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
         if (st == SS_TRAILER) {
             if (!P.segment_mode && result == ST_FINISHED) {
                 // back to a byte boundary, then the container trailer
-                br.skip((uint32_t)((0 - br.consumed) & 7));
+                br.skip((uint32_t)((0 - br.consumed()) & 7));
                 if (wrap == 1) {
                     uint32_t v = 0;
                     for (int i = 0; i < 4; i++) v = (v << 8) | br.get_byte();
@@ -773,7 +777,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
             P.out_lens[unit] = out_pos;
             P.statuses[unit] = result;
             if (P.in_consumed) {
-                uint64_t c = (br.consumed + 7) >> 3;
+                uint64_t c = (br.consumed() + 7) >> 3;
                 P.in_consumed[unit] = c < in_len ? c : in_len;
             }
             if (P.checks) { P.checks[2 * unit] = adler; P.checks[2 * unit + 1] = crc; }

@@ -1,6 +1,7 @@
 // sim_kernels.cpp — runs the product's kernel sources on the CPU emulator (tests only; see cusim.h).
 #include "cusim.h"
 #include "../../compu_b200/csrc/inflate_kernel.cuh"
+#include "../../compu_b200/csrc/inflate_lane_kernel.cuh"
 
 using namespace czk;
 
@@ -27,6 +28,8 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
         case 4: run_inflate<4, 2>(P, grid); break;
         case 8: run_inflate<8, 1>(P, grid); break;
         case 32: run_inflate<32, 1>(P, grid); break;
+        case -9: cusim::launch(grid, 2 * 32, inflate_lane_smem_bytes<9, 8, 2>(), inflate_lane_kernel<9, 8, 2>, P); break;
+        case -8: cusim::launch(grid, 1 * 32, inflate_lane_smem_bytes<8, 7, 1>(), inflate_lane_kernel<8, 7, 1>, P); break;
         default: return -1;
     }
     return 0;
