@@ -5,6 +5,7 @@
 #include "host_common.h"
 #include "inflate_kernel.cuh"
 #include "inflate_lane_kernel.cuh"
+#include "inflate_lc_kernel.cuh"
 
 namespace czh {
 
@@ -55,11 +56,32 @@ static int launch_lane(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams
     return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
 }
 
+// "one lane = one stream, canonical decode" variant: W warps per CTA, one CTA per SM
+template <int W>
+static int launch_lc(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams &P) {
+    auto kern = czk::inflate_lc_kernel<W>;
+    const size_t smem = czk::inflate_lc_smem_bytes<W>();
+    static bool configured[64] = {};
+    if (!configured[ctx->dev & 63]) {
+        if (!CZ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return CZ_E_MEM;
+        configured[ctx->dev & 63] = true;
+    }
+    int per_sm = 0;
+    if (!CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, smem))) return CZ_E_MEM;
+    if (per_sm < 1) { set_error("inflate lc kernel <%d> does not fit on an SM", W); return CZ_E_MEM; }
+    uint64_t ctas_needed = (P.n + 32 * W - 1) / (32 * W);
+    uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
+    if (ctas_needed < grid) grid = ctas_needed;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, W * 32, smem, st>>>(P);
+    return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
+}
+
 static InflateCfg g_cfg = {0, 0};
 
 static InflateCfg pick_cfg() {
     if (g_cfg.D == 0) {
-        InflateCfg c{-9, 8};  // lane kernel, 2^9 litlen / 2^8 distance primary tables
+        InflateCfg c{-1, 10};  // lane-per-stream canonical-decode kernel, 10 warps (320 streams) per SM
         if (const char *e = getenv("CZ_INFLATE_CFG")) {
             int d = 0, w = 0;
             if (sscanf(e, "%d,%d", &d, &w) == 2) { c.D = d; c.W = w; }
@@ -89,7 +111,12 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
     CZ_CFG(1, 8); CZ_CFG(2, 8); CZ_CFG(4, 7); CZ_CFG(4, 4); CZ_CFG(8, 7); CZ_CFG(8, 4); CZ_CFG(8, 2); CZ_CFG(16, 3);
     CZ_CFG(16, 1); CZ_CFG(32, 1);
 #undef CZ_CFG
-    // negative D selects the lane-per-stream kernel: D = -LB, W = DB
+    // D = -1: lane-per-stream canonical-decode kernel with W warps per CTA
+    if (c.D == -1 && c.W == 10) return launch_lc<10>(st, ctx, P);
+    if (c.D == -1 && c.W == 8) return launch_lc<8>(st, ctx, P);
+    if (c.D == -1 && c.W == 5) return launch_lc<5>(st, ctx, P);
+    if (c.D == -1 && c.W == 4) return launch_lc<4>(st, ctx, P);
+    // other negative D select the table-based lane-per-stream kernel: D = -LB, W = DB
     if (c.D == -9 && c.W == 8) return launch_lane<9, 8, 3>(st, ctx, P);
     if (c.D == -8 && c.W == 7) return launch_lane<8, 7, 4>(st, ctx, P);
     if (c.D == -10 && c.W == 8) return launch_lane<10, 8, 2>(st, ctx, P);

@@ -2,6 +2,7 @@
 #include "cusim.h"
 #include "../../compu_b200/csrc/inflate_kernel.cuh"
 #include "../../compu_b200/csrc/inflate_lane_kernel.cuh"
+#include "../../compu_b200/csrc/inflate_lc_kernel.cuh"
 
 using namespace czk;
 
@@ -28,6 +29,7 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
         case 4: run_inflate<4, 2>(P, grid); break;
         case 8: run_inflate<8, 1>(P, grid); break;
         case 32: run_inflate<32, 1>(P, grid); break;
+        case -1: cusim::launch(grid, 2 * 32, inflate_lc_smem_bytes<2>(), inflate_lc_kernel<2>, P); break;
         case -9: cusim::launch(grid, 2 * 32, inflate_lane_smem_bytes<9, 8, 2>(), inflate_lane_kernel<9, 8, 2>, P); break;
         case -8: cusim::launch(grid, 1 * 32, inflate_lane_smem_bytes<8, 7, 1>(), inflate_lane_kernel<8, 7, 1>, P); break;
         default: return -1;
