@@ -60,6 +60,10 @@ DeviceCtx *device_ctx(int dev) {
     int prev = 0;
     cudaGetDevice(&prev);
     if (!CZ_CUDA(cudaSetDevice(dev))) return nullptr;
+    if (const char *g = getenv("CZ_L2_FETCH")) {  // experiment knob: L2 fetch granularity hint (32/64/128 bytes)
+        int v = atoi(g);
+        if (v == 32 || v == 64 || v == 128) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
+    }
     czk::CrcTables t;
     czk::init_crc_tables(&t);
     bool ok = CZ_CUDA(cudaMalloc(&c.d_crc, sizeof t)) && CZ_CUDA(cudaMemcpy(c.d_crc, &t, sizeof t, cudaMemcpyHostToDevice));

@@ -81,7 +81,7 @@ static InflateCfg g_cfg = {0, 0};
 
 static InflateCfg pick_cfg() {
     if (g_cfg.D == 0) {
-        InflateCfg c{-1, 10};  // lane-per-stream canonical-decode kernel, 10 warps (320 streams) per SM
+        InflateCfg c{-1, 14};  // lane-per-stream canonical-decode kernel, 14 warps (448 streams) per SM
         if (const char *e = getenv("CZ_INFLATE_CFG")) {
             int d = 0, w = 0;
             if (sscanf(e, "%d,%d", &d, &w) == 2) { c.D = d; c.W = w; }
@@ -112,8 +112,12 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
     CZ_CFG(16, 1); CZ_CFG(32, 1);
 #undef CZ_CFG
     // D = -1: lane-per-stream canonical-decode kernel with W warps per CTA
+    if (c.D == -1 && c.W == 14) return launch_lc<14>(st, ctx, P);
+    if (c.D == -1 && c.W == 12) return launch_lc<12>(st, ctx, P);
     if (c.D == -1 && c.W == 10) return launch_lc<10>(st, ctx, P);
     if (c.D == -1 && c.W == 8) return launch_lc<8>(st, ctx, P);
+    if (c.D == -1 && c.W == 7) return launch_lc<7>(st, ctx, P);
+    if (c.D == -1 && c.W == 6) return launch_lc<6>(st, ctx, P);
     if (c.D == -1 && c.W == 5) return launch_lc<5>(st, ctx, P);
     if (c.D == -1 && c.W == 4) return launch_lc<4>(st, ctx, P);
     // other negative D select the table-based lane-per-stream kernel: D = -LB, W = DB

@@ -8,8 +8,8 @@
 // So this variant keeps NO lookup table: Huffman codes are decoded canonically. The 15 per-length code limits of the
 // literal/length code and of the distance code live in REGISTERS (30 registers per lane); a symbol is found with 15
 // independent compares (code length = 1 + #limits <= the bit-reversed 16-bit window), one 32-byte base-offset lookup
-// and one lookup in the canonically sorted symbol array. Per-stream shared memory drops to 704 bytes, so 10 warps =
-// 320 concurrent streams run per SM and the per-symbol latency chain is hidden by other warps.
+// and one lookup in the canonically sorted symbol array. Per-stream shared memory drops to 448 bytes, so 14 warps =
+// 448 concurrent streams run per SM and the per-symbol latency chain is hidden by other warps.
 //
 // Everything on the per-symbol path is lane-local (decode, literal store, LZ77 copy, running Adler-32 / CRC-32); only
 // table construction and stored-block copies are warp-cooperative. Contract, status numbering and zlib's error order
@@ -20,16 +20,16 @@
 namespace czk {
 
 struct LcSlot {
-    // while a block header is parsed: u16 cl_tab[128] at byte 0, u8 lens[320] at byte 256 (both inside lit_sorted)
-    uint16_t lit_sorted[288];
-    uint16_t lit_base[16];   // offs[len] - first_code[len]  (mod 2^16)
-    uint16_t dist_base[16];
+    // while a block header is parsed: u8 cl_tab[128] at byte 0, u8 lens[320] at byte 128
+    uint8_t lit_sorted[288];  // low 8 bits of the canonically sorted literal/length symbols
+    uint32_t lit_info[16];    // per code length: (offs - first_code) mod 2^16 | (first sorted index holding a symbol >= 256) << 16
+    uint16_t dist_base[16];   // offs[len] - first_code[len]  (mod 2^16)
     uint8_t dist_sorted[32];
     uint8_t pad[32];
 };
-static_assert(sizeof(LcSlot) == 704, "LcSlot layout");
+static_assert(sizeof(LcSlot) == 448, "LcSlot layout");
 
-__device__ __forceinline__ uint8_t *lc_lens(LcSlot &sm) { return (uint8_t *)&sm + 256; }
+__device__ __forceinline__ uint8_t *lc_lens(LcSlot &sm) { return (uint8_t *)&sm + 128; }
 
 // length base (9 bits) | extra-bit count << 9 for length symbols 257..285, kept in shared memory per CTA
 __host__ __device__ inline uint32_t lc_len_info(uint32_t c) {
@@ -54,13 +54,13 @@ __device__ __forceinline__ int lc_build(LcSlot &sm, uint32_t nlit, uint32_t ndis
 #pragma unroll
     for (int which = 0; which < 2; which++) {
         const bool is_dist = which == 1;
-        uint16_t *base_arr = is_dist ? sm.dist_base : sm.lit_base;
         if (lane < 16) { wcnt[lane] = 0; wrun[lane] = 0; }
+        if (lane >= 16) wrun[lane] = 0;  // wrun[16..31]: per length, number of symbols < 256
         __syncwarp();
         if (is_dist) { if (dl) atomicAdd(&wcnt[dl], 1u); }
         else {
 #pragma unroll
-            for (int r = 0; r < 9; r++) if (ll[r]) atomicAdd(&wcnt[ll[r]], 1u);
+            for (int r = 0; r < 9; r++) if (ll[r]) { atomicAdd(&wcnt[ll[r]], 1u); if (r < 8) atomicAdd(&wrun[16 + ll[r]], 1u); }
         }
         __syncwarp();
         int left = 1;
@@ -79,7 +79,10 @@ __device__ __forceinline__ int lc_build(LcSlot &sm, uint32_t nlit, uint32_t ndis
             if (c) maxlen = len;
         }
         if (over || (left > 0 && maxlen > 1)) rc = ST_E_DATA;  // zlib inflate_table(): over-subscribed / incomplete set
-        if (lane >= 1 && lane < 16) base_arr[lane] = (uint16_t)(my_off - my_first);
+        if (lane >= 1 && lane < 16) {
+            if (is_dist) sm.dist_base[lane] = (uint16_t)(my_off - my_first);
+            else sm.lit_info[lane] = ((my_off - my_first) & 0xffffu) | ((my_off + wrun[16 + lane]) << 16);
+        }
         __syncwarp();
         const int rounds = is_dist ? 1 : 9;
 #pragma unroll
@@ -97,7 +100,7 @@ __device__ __forceinline__ int lc_build(LcSlot &sm, uint32_t nlit, uint32_t ndis
 #pragma unroll
                 for (uint32_t len = 1; len <= 15; len++) offs_l += len < l ? wcnt[len] : 0;
                 uint32_t pos = offs_l + base + rank;
-                if (is_dist) sm.dist_sorted[pos & 31] = (uint8_t)sym; else if (pos < 288) sm.lit_sorted[pos] = (uint16_t)sym;
+                if (is_dist) sm.dist_sorted[pos & 31] = (uint8_t)sym; else if (pos < 288) sm.lit_sorted[pos] = (uint8_t)sym;
             }
             __syncwarp();
         }
@@ -148,7 +151,7 @@ __device__ inline int lc_parse_dynamic(BitReader &br, LcSlot &sm, uint32_t &nlit
         code = (code + c) << 1;
     }
     if (left > 0) return ST_E_DATA;  // zlib: an incomplete code-length code is always an error
-    uint16_t *cl_tab = sm.lit_sorted;  // 128 entries = 256 bytes
+    uint8_t *cl_tab = sm.lit_sorted;  // 128 one-byte entries: symbol << 3 | length
     for (uint32_t i = 0; i < 128; i++) cl_tab[i] = 0;
     for (uint32_t s = 0; s < 19; s++) {
         uint32_t l = (uint32_t)(cl_lens >> (3 * s)) & 7;
@@ -156,7 +159,7 @@ __device__ inline int lc_parse_dynamic(BitReader &br, LcSlot &sm, uint32_t &nlit
         uint32_t c = (uint32_t)(nextp >> (8 * l)) & 0xff;
         nextp += 1ull << (8 * l);
         uint32_t rev = __brev(c) >> (32 - l);
-        for (uint32_t idx = rev; idx < 128; idx += (1u << l)) cl_tab[idx] = (uint16_t)((s << 3) | l);
+        for (uint32_t idx = rev; idx < 128; idx += (1u << l)) cl_tab[idx] = (uint8_t)((s << 3) | l);
     }
     uint32_t total = nlit + ndist, i = 0, prev = 0;
     uint8_t *lens = lc_lens(sm);
@@ -193,11 +196,11 @@ template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) inflate_lc_kernel(InflateParams P) {
     CZ_DYNAMIC_SMEM(smem_raw);
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // layout: [crc table 1 KB] [length info 128 B] [per-warp scratch 128 B each] [WARPS*32 slots]
+    // layout: [crc table 1 KB] [length info 128 B] [per-warp scratch 256 B each] [WARPS*32 slots]
     uint32_t *crc_tab = (uint32_t *)smem_raw;
     uint16_t *len_info = (uint16_t *)(smem_raw + 1024);
-    uint32_t *wscr = (uint32_t *)(smem_raw + 1152) + warp * 32;
-    LcSlot *slots = (LcSlot *)(smem_raw + 1152 + WARPS * 128) + (size_t)warp * 32;
+    uint32_t *wscr = (uint32_t *)(smem_raw + 1152) + warp * 64;  // wcnt[16] wrun[16] wnlo[16] pad
+    LcSlot *slots = (LcSlot *)(smem_raw + 1152 + WARPS * 256) + (size_t)warp * 32;
     LcSlot &my = slots[lane];
     if (P.crc)
         for (uint32_t i = threadIdx.x; i < 256; i += WARPS * 32) crc_tab[i] = P.crc->table[i];
@@ -313,7 +316,9 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lc_kernel(InflateParams P)
                     st = SS_FINISH;
                     break;
                 }
-                uint32_t sym = my.lit_sorted[((v >> (16 - cl)) + my.lit_base[cl]) & 0x1ff];
+                uint32_t info = my.lit_info[cl];
+                uint32_t idx = ((v >> (16 - cl)) + info) & 0xffffu;
+                uint32_t sym = my.lit_sorted[idx < 288 ? idx : 287] | (idx >= (info >> 16) ? 256u : 0u);
                 br.skip(cl);
                 if (sym < 256) {  // literal
                     if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
@@ -494,6 +499,6 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lc_kernel(InflateParams P)
 }
 
 template <int WARPS>
-constexpr size_t inflate_lc_smem_bytes() { return 1152 + WARPS * 128 + sizeof(LcSlot) * 32 * (size_t)WARPS; }
+constexpr size_t inflate_lc_smem_bytes() { return 1152 + WARPS * 256 + sizeof(LcSlot) * 32 * (size_t)WARPS; }
 
 }  // namespace czk
