@@ -46,8 +46,8 @@ SIGNATURES = {
     "cz_inflate_segments_device": (ci, [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, u64]),
     "cz_deflate_max_segment": (u64, []),
     "cz_deflate_segment_bound": (u64, [u64]),
-    "cz_deflate_workspace_bytes": (u64, [sz]),
-    "cz_deflate_segments_device": (ci, [vp, sz, vp, vp, vp, vp, vp, vp, vp, ci, ci, vp, u64]),
+    "cz_deflate_workspace_bytes": (u64, [sz, u64]),
+    "cz_deflate_segments_device": (ci, [vp, sz, vp, vp, u64, vp, vp, vp, vp, vp, ci, ci, vp, u64]),
     "cz_adler32_combine": (u32, [u32, u32, u64]),
     "cz_crc32_combine": (u32, [u32, u32, u64]),
     "cz_synth_model_bytes": (u64, []),

@@ -9,6 +9,12 @@
 
 #ifdef CUSIM
 #include "cusim.h"
+#elif defined(CZK_MODEL)
+// host-only build of the shared __host__ __device__ decision code (tests/model); no CUDA headers needed
+#ifndef __host__
+#define __host__
+#define __device__
+#endif
 #else
 #include <cuda_runtime.h>
 #define CZ_DYNAMIC_SMEM(name) extern __shared__ __align__(16) uint8_t name[]

@@ -1,0 +1,516 @@
+// deflate_kernels.cuh — segmented DEFLATE encoder for sm_100a as a chain of data-parallel passes.
+//
+// Replaces what compu outsources to L0 `deflate()` behind encode_fn (/root/reference/src/encoder/zlib_ng.rs:90-92 ->
+// src/encoder/mod.rs:334-370). The input of every unit (buffer to compress) is cut into segments of at most 1 MiB; each
+// segment is compressed with no history from its neighbours and ends with an empty stored block (what Z_FULL_FLUSH
+// emits), so the concatenation  header | seg0 | seg1 | ... | 03 00 | trailer  is ONE valid zlib/gzip/raw stream
+//  and every segment can later be inflated on its own.
+//
+// Data layout in HBM (all offsets relative to seg_off[0]; "B" = bytes of input in the launch):
+//   in        B bytes        segments are contiguous: segment s = in[seg_off[s] .. seg_off[s+1])
+//   prevd     2B bytes       hash-chain links (distance to the previous position with the same 4-byte hash)
+//   match     4B bytes       best match per position (len | dist << 9); overwritten in place by the token list
+//   blocks    (B >> 14) + nseg + 1 slots: segment s owns slots [blk_first(s), blk_first(s+1)); a block = 16384 tokens
+//             per slot: blk_end (input offset where the block ends), freqs (320 counters), BlockPlan (codes + header)
+//
+// Passes (all intermediates stay in HBM; the match search K2 dominates):
+//   K0 checksum   warp per segment      Adler-32 / CRC-32 of the segment's input (combined per unit in K5c)
+//   K1 chains     warp per segment      prevd[]: 32 positions per step, __match_any_sync inside the step, a 16 KB
+//                                       shared-memory head table across steps (result == sequential insertion)
+//   K2 match      thread per position   best (length, distance) by walking the chain (deflate_core.cuh find_match)
+//   K3 parse      thread per segment    one-step-lazy parse into tokens, in place; cuts blocks of 16384 tokens
+//   K4a histogram CTA per block         literal/length and distance symbol counts (shared-memory atomics)
+//   K4b plan      thread per block      length-limited Huffman codes, stored/fixed/dynamic choice, rendered header
+//   K5a layout    thread per segment    bit offset of every block, size of the segment
+//   K5c sizes     thread per unit       size of the unit's stream, combined checksums, capacity check
+//   K5s scan      one CTA               (packed output only) exclusive scan of the unit sizes -> output positions
+//   K5d frame     thread per unit       container header, flush markers, final block, trailer; segment positions
+//   K5b zero      thread per block      clears the bytes that two blocks share (they are written with atomicOr)
+//   K6 emit       CTA per block         token -> code bits, block-wide prefix scan of the bit lengths, bits assembled in
+//                                       shared memory and written out as whole bytes
+#pragma once
+#include "deflate_core.cuh"
+#include "inflate_kernel.cuh"  // warp_adler32 / warp_crc32_pieces / crc32_serial
+
+namespace czk {
+
+#define CZK_SEG_MAX (1u << 20)  // largest segment
+#define CZK_FREQ_STRIDE 320u    // 288 literal/length slots + 32 distance slots per block
+
+struct SegState {
+    uint32_t ntok, nblk;
+    uint32_t adler, crc;
+    uint64_t out_bytes;  // bytes of the segment including its flush marker
+    uint64_t out_off;    // absolute byte offset of the segment in the output buffer (~0: unit not written)
+    uint64_t body_bits;  // bits of all blocks (before the flush marker)
+};
+
+struct DeflateParams {
+    const uint8_t *in;             // in + seg_off[s] is the first byte of segment s
+    uint8_t *out;
+    const uint64_t *seg_off;       // nseg+1
+    uint32_t nseg, n_units, n_slots;
+    const uint32_t *unit_seg;      // n_units+1: first segment of each unit; null => unit u is segment u
+    const uint64_t *unit_out_off;  // n_units+1: output slots (capacity of unit u = unit_out_off[u+1]-unit_out_off[u])
+    uint64_t *unit_out_pos;        // null: unit u is written at its slot; else at out + unit_out_pos[u] (packed, by K5s)
+    uint64_t *unit_out_len;        // size of the unit's stream (also when it did not fit)
+    int32_t *unit_status;
+    uint32_t *unit_checks;         // 2 per unit {adler32, crc32} of the unit's input, or null
+    uint64_t *seg_out_bytes;       // per segment compressed size (incl. flush marker) or null — the side index
+    uint64_t *total_out;           // packed mode: total bytes written (1 value)
+    SegState *st;                  // nseg
+    uint16_t *prevd;
+    uint32_t *match;
+    uint32_t *blk_end;             // n_slots
+    uint32_t *freqs;               // n_slots * CZK_FREQ_STRIDE
+    BlockPlan *plans;              // n_slots
+    const CrcTables *crc;
+    DeflateTuning tune;
+    int32_t window_bits;  // -15 raw, 15 zlib, 31 gzip
+    int32_t level;
+    int32_t piece_mode;   // 1: units are raw pieces of a longer stream: no container, no final block
+    int32_t check_kind;   // bit0 Adler-32, bit1 CRC-32
+};
+
+__device__ __forceinline__ uint64_t seg_base(const DeflateParams &P, uint32_t seg) { return P.seg_off[seg] - P.seg_off[0]; }
+__device__ __forceinline__ uint32_t seg_len(const DeflateParams &P, uint32_t seg) { return (uint32_t)(P.seg_off[seg + 1] - P.seg_off[seg]); }
+// first block slot of a segment: a closed form that leaves every segment ceil(len / 16384) + 1 > #blocks slots
+__device__ __forceinline__ uint32_t blk_first(const DeflateParams &P, uint32_t seg) { return (uint32_t)(seg_base(P, seg) >> 14) + seg; }
+
+// slot -> (segment, block index inside it); false if the slot is unused
+__device__ inline bool slot_to_block(const DeflateParams &P, uint32_t slot, uint32_t &seg, uint32_t &b) {
+    uint32_t lo = 0, hi = P.nseg;  // last segment with blk_first <= slot
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (blk_first(P, mid) <= slot) lo = mid; else hi = mid;
+    }
+    seg = lo;
+    b = slot - blk_first(P, lo);
+    return b < P.st[lo].nblk;
+}
+
+// ------------------------------------------------------------------ K0
+__global__ void __launch_bounds__(128) deflate_checksum_kernel(DeflateParams P) {
+    __shared__ uint32_t crc_tab[256 + 34];
+    for (uint32_t i = threadIdx.x; i < 256 + 34; i += 128) crc_tab[i] = i < 256 ? P.crc->table[i] : P.crc->pow128[i - 256];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t seg = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (seg >= P.nseg) return;
+    const uint8_t *p = P.in + P.seg_off[seg];
+    const uint32_t n = seg_len(P, seg);
+    uint32_t a = 1, c = 0;
+    if (P.check_kind & 1) {
+        for (uint32_t o = 0; o < n; o += 8192) a = warp_adler32(a, p + o, n - o < 8192 ? n - o : 8192, lane);
+    }
+    if (P.check_kind & 2) {
+        uint32_t o = 0;
+        while (n - o >= 128) {
+            uint32_t q = (n - o) >> 7;
+            if (q > 32) q = 32;
+            c = warp_crc32_pieces(c, p + o, q, crc_tab, crc_tab + 256, lane);
+            o += q * 128;
+        }
+        if (o < n) {
+            uint32_t c2 = 0;
+            if (lane == 0) c2 = crc32_serial(c, p + o, n - o, crc_tab);
+            c = __shfl_sync(CZK_FULL, c2, 0);
+        }
+    }
+    if (lane == 0) { P.st[seg].adler = a; P.st[seg].crc = c; }
+}
+
+// ------------------------------------------------------------------ K1
+// One warp per segment. Step k handles positions 32k..32k+31. Result == inserting the positions one by one.
+__global__ void __launch_bounds__(32) deflate_chain_kernel(DeflateParams P) {
+    __shared__ uint16_t head[1u << CZK_HASH_BITS];
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t seg = blockIdx.x; seg < P.nseg; seg += gridDim.x) {
+        const uint8_t *s = P.in + P.seg_off[seg];
+        const uint32_t n = seg_len(P, seg);
+        uint16_t *pd = P.prevd + seg_base(P, seg);
+        __syncwarp();
+        for (uint32_t i = lane; i < (1u << CZK_HASH_BITS); i += 32) head[i] = 0xffff;
+        __syncwarp();
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t pos = base + lane;
+            const bool valid = pos + 4 <= n;
+            uint32_t v = 0;
+            if (valid) v = load32(s + pos);
+            // lanes without 4 bytes left get a private pseudo-hash so they never group with real ones
+            const uint32_t h = valid ? hash4(v) : (0x10000u + lane);
+            const uint32_t grp = __match_any_sync(CZK_FULL, h);
+            uint32_t d = 0;
+            if (valid) {
+                const uint32_t lower = grp & ((1u << lane) - 1u);
+                if (lower) d = lane - (31u - (uint32_t)__clz((int)lower));  // nearest earlier lane with the same hash
+                else {
+                    const uint32_t dd = (pos - (uint32_t)head[h]) & 0xffffu;
+                    // stale or never-written entries alias to some other position: keep the link only if that
+                    // position really has this hash (then it IS the most recent one, see deflate_model.cpp)
+                    if (dd >= 1 && dd < CZK_WINDOW && dd <= pos && hash4(load32(s + pos - dd)) == h) d = dd;
+                }
+            }
+            if (pos < n) pd[pos] = (uint16_t)d;
+            __syncwarp();
+            if (valid && (grp >> lane) <= 1u) head[h] = (uint16_t)(pos & 0xffffu);  // highest lane of the group
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------ K2
+// 256 consecutive input bytes per CTA; a tile may straddle segment boundaries.
+__global__ void __launch_bounds__(256) deflate_match_kernel(DeflateParams P, uint64_t total_bytes) {
+    __shared__ uint32_t s_seg;
+    const uint64_t g0 = (uint64_t)blockIdx.x * 256;
+    if (threadIdx.x == 0) {
+        uint32_t lo = 0, hi = P.nseg;  // last segment with base <= g0
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (seg_base(P, mid) <= g0) lo = mid; else hi = mid;
+        }
+        s_seg = lo;
+    }
+    __syncthreads();
+    const uint64_t g = g0 + threadIdx.x;
+    if (g >= total_bytes) return;
+    uint32_t seg = s_seg;
+    while (seg + 1 < P.nseg && seg_base(P, seg + 1) <= g) seg++;
+    const uint64_t base = seg_base(P, seg);
+    const uint32_t pos = (uint32_t)(g - base);
+    P.match[g] = P.tune.level0 ? 0u : find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune);
+}
+
+// ------------------------------------------------------------------ K3
+__global__ void __launch_bounds__(32) deflate_parse_kernel(DeflateParams P) {
+    const uint32_t seg = blockIdx.x * 32 + threadIdx.x;
+    if (seg >= P.nseg) return;
+    const uint64_t base = seg_base(P, seg);
+    const uint32_t first = blk_first(P, seg), cap = blk_first(P, seg + 1) - first;
+    uint32_t nb = 0;
+    uint32_t nt = parse_segment(P.in + P.seg_off[seg], seg_len(P, seg), P.match + base, P.tune, P.blk_end + first, cap, &nb);
+    P.st[seg].ntok = nt;
+    P.st[seg].nblk = nb;
+}
+
+// ------------------------------------------------------------------ K4a
+__global__ void __launch_bounds__(128) deflate_hist_kernel(DeflateParams P) {
+    __shared__ uint32_t hist[CZK_FREQ_STRIDE];
+    __shared__ uint32_t s_seg, s_b, s_ok;
+    if (threadIdx.x == 0) { uint32_t sg, b; s_ok = slot_to_block(P, blockIdx.x, sg, b); s_seg = sg; s_b = b; }
+    for (uint32_t i = threadIdx.x; i < CZK_FREQ_STRIDE; i += 128) hist[i] = 0;
+    __syncthreads();
+    if (!s_ok) return;
+    const uint32_t seg = s_seg, b = s_b;
+    const uint32_t t0 = b * CZK_BLOCK_TOKENS;
+    uint32_t t1 = t0 + CZK_BLOCK_TOKENS;
+    if (t1 > P.st[seg].ntok) t1 = P.st[seg].ntok;
+    const uint32_t *tok = P.match + seg_base(P, seg);
+    for (uint32_t k = t0 + threadIdx.x; k < t1; k += 128) {
+        uint32_t t = tok[k], len = t & 0x1ff;
+        if (len < CZK_MIN_MATCH) atomicAdd(&hist[t >> 9], 1u);
+        else { atomicAdd(&hist[len_code(len)], 1u); atomicAdd(&hist[288 + dist_code(t >> 9)], 1u); }
+    }
+    __syncthreads();
+    uint32_t *f = P.freqs + (size_t)blockIdx.x * CZK_FREQ_STRIDE;
+    for (uint32_t i = threadIdx.x; i < CZK_FREQ_STRIDE; i += 128) f[i] = i == 256 ? 1u : hist[i];
+}
+
+// ------------------------------------------------------------------ K4b
+__global__ void __launch_bounds__(32) deflate_plan_kernel(DeflateParams P) {
+    const uint32_t slot = blockIdx.x * 32 + threadIdx.x;
+    if (slot >= P.n_slots) return;
+    uint32_t seg, b;
+    if (!slot_to_block(P, slot, seg, b)) return;
+    BlockPlan &bp = P.plans[slot];
+    bp.tok_begin = b * CZK_BLOCK_TOKENS;
+    uint32_t t1 = bp.tok_begin + CZK_BLOCK_TOKENS;
+    bp.tok_end = t1 < P.st[seg].ntok ? t1 : P.st[seg].ntok;
+    bp.in_begin = b ? P.blk_end[slot - 1] : 0;
+    bp.in_end = P.blk_end[slot];
+    HuffScratch hs;
+    const uint32_t *f = P.freqs + (size_t)slot * CZK_FREQ_STRIDE;
+    plan_block(f, f + 288, bp, hs, P.tune);
+}
+
+// bits a block occupies when it starts at bit position `bits` (stored blocks pad to a byte boundary per piece)
+__host__ __device__ inline uint64_t block_end_bit(const BlockPlan &bp, uint64_t bits) {
+    if (bp.btype != 0) return bits + bp.hdr_bits + bp.body_bits;
+    uint32_t left = bp.in_end - bp.in_begin;
+    do {
+        uint32_t k = left > 65535 ? 65535 : left;
+        bits = ((bits + 3 + 7) & ~(uint64_t)7) + 32 + 8ull * k;
+        left -= k;
+    } while (left);
+    return bits;
+}
+
+// ------------------------------------------------------------------ K5a
+__global__ void __launch_bounds__(32) deflate_seg_layout_kernel(DeflateParams P) {
+    const uint32_t seg = blockIdx.x * 32 + threadIdx.x;
+    if (seg >= P.nseg) return;
+    uint64_t bits = 0;  // a segment starts on a byte boundary
+    const uint32_t nb = P.st[seg].nblk, first = blk_first(P, seg);
+    for (uint32_t b = 0; b < nb; b++) {
+        BlockPlan &bp = P.plans[first + b];
+        bp.bit_off = bits;
+        bits = block_end_bit(bp, bits);
+    }
+    P.st[seg].body_bits = bits;
+    P.st[seg].out_bytes = ((bits + 3 + 7) >> 3) + 4;  // + empty stored block: 3 bits, pad, 00 00 ff ff
+}
+
+__device__ __forceinline__ void unit_segs(const DeflateParams &P, uint32_t u, uint32_t &s0, uint32_t &s1) {
+    if (P.unit_seg) { s0 = P.unit_seg[u]; s1 = P.unit_seg[u + 1]; }
+    else { s0 = u; s1 = u + 1; }
+}
+__device__ __forceinline__ uint32_t container_hdr(const DeflateParams &P) {
+    const int wb = P.piece_mode ? -15 : P.window_bits;
+    return wb == 15 ? 2 : wb > 15 ? 10 : 0;
+}
+__device__ __forceinline__ uint32_t container_trl(const DeflateParams &P) {
+    const int wb = P.piece_mode ? -15 : P.window_bits;
+    return wb == 15 ? 4 : wb > 15 ? 8 : 0;
+}
+
+// ------------------------------------------------------------------ K5c
+__global__ void __launch_bounds__(32) deflate_unit_size_kernel(DeflateParams P) {
+    const uint32_t u = blockIdx.x * 32 + threadIdx.x;
+    if (u >= P.n_units) return;
+    uint32_t s0, s1;
+    unit_segs(P, u, s0, s1);
+    const uint64_t cap = P.unit_out_off[u + 1] - P.unit_out_off[u];
+    uint64_t total = container_hdr(P);
+    for (uint32_t s = s0; s < s1; s++) total += P.st[s].out_bytes;
+    total += (P.piece_mode ? 0 : 2) + container_trl(P);
+    P.unit_out_len[u] = total;
+    P.unit_status[u] = total > cap ? 1 /* CZ_ENCODE_NEED_OUTPUT: nothing of this unit is written */ : 2 /* FINISHED */;
+    if (P.unit_checks) {
+        // checksums of the unit's input: fold of the per-segment values
+        uint32_t adler = 1, crc = 0;
+        uint32_t pw_len = 0xffffffffu, pw = 0;  // cached x^(8 len) for the CRC combine (segments share one length)
+        for (uint32_t s = s0; s < s1; s++) {
+            const uint32_t len = seg_len(P, s);
+            if (P.check_kind & 1) adler = adler32_combine_u(adler, P.st[s].adler, len);
+            if (P.check_kind & 2) {
+                if (len != pw_len) { pw = crc_xpow8n(len); pw_len = len; }
+                crc = crc_mulmod(pw, crc) ^ P.st[s].crc;
+            }
+        }
+        P.unit_checks[2 * u] = adler;
+        P.unit_checks[2 * u + 1] = crc;
+    }
+}
+
+// ------------------------------------------------------------------ K5s
+// Exclusive scan of the sizes of the units that fit -> packed output positions. One CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) deflate_scan_kernel(DeflateParams P) {
+    __shared__ uint64_t part[1024];
+    const uint32_t t = threadIdx.x, n = P.n_units;
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t b = t * per, e = b + per < n ? b + per : n;
+    uint64_t sum = 0;
+    for (uint32_t u = b; u < e; u++) sum += P.unit_status[u] == 2 ? P.unit_out_len[u] : 0;
+    part[t] = sum;
+    __syncthreads();
+    for (uint32_t d = 1; d < 1024; d <<= 1) {
+        uint64_t v = t >= d ? part[t - d] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    uint64_t run = part[t] - sum;
+    for (uint32_t u = b; u < e; u++) {
+        P.unit_out_pos[u] = run;
+        run += P.unit_status[u] == 2 ? P.unit_out_len[u] : 0;
+    }
+    if (t == 1023 && P.total_out) *P.total_out = part[1023];
+}
+
+// ------------------------------------------------------------------ K5d
+__global__ void __launch_bounds__(32) deflate_unit_frame_kernel(DeflateParams P) {
+    const uint32_t u = blockIdx.x * 32 + threadIdx.x;
+    if (u >= P.n_units) return;
+    uint32_t s0, s1;
+    unit_segs(P, u, s0, s1);
+    if (P.unit_status[u] != 2) {
+        for (uint32_t s = s0; s < s1; s++) P.st[s].out_off = ~0ull;
+        return;
+    }
+    const uint64_t o0 = P.unit_out_pos ? P.unit_out_pos[u] : P.unit_out_off[u];
+    const int wb = P.piece_mode ? -15 : P.window_bits;
+    uint8_t *o = P.out + o0;
+    uint64_t pos = 0;
+    if (wb == 15) {
+        // CMF = 0x78 (deflate, 32 KiB window); FLG: FLEVEL by level like zlib, FCHECK makes (CMF<<8|FLG) % 31 == 0
+        uint32_t lvl = P.level < 0 ? 6 : P.level;
+        uint32_t flevel = lvl < 2 ? 0 : lvl < 6 ? 1 : lvl == 6 ? 2 : 3;
+        uint32_t h = (0x78u << 8) | (flevel << 6);
+        h += 31 - (h % 31);
+        o[0] = (uint8_t)(h >> 8);
+        o[1] = (uint8_t)h;
+        pos = 2;
+    } else if (wb > 15) {
+        uint32_t lvl = P.level < 0 ? 6 : P.level;
+        const uint8_t g[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, (uint8_t)(lvl == 9 ? 2 : lvl == 1 ? 4 : 0), 3};
+        for (int i = 0; i < 10; i++) o[i] = g[i];
+        pos = 10;
+    }
+    for (uint32_t s = s0; s < s1; s++) {
+        P.st[s].out_off = o0 + pos;
+        if (P.seg_out_bytes) P.seg_out_bytes[s] = P.st[s].out_bytes;
+        // flush marker of the segment: bytes wholly owned by it are written here, the shared byte is OR-ed by emit
+        const uint64_t bits = P.st[s].body_bits;
+        const uint64_t mark = (bits + 3 + 7) >> 3;  // first byte of 00 00 ff ff
+        for (uint64_t k = (bits + 7) >> 3; k < mark; k++) o[pos + k] = 0;
+        o[pos + mark] = 0; o[pos + mark + 1] = 0; o[pos + mark + 2] = 0xff; o[pos + mark + 3] = 0xff;
+        pos += P.st[s].out_bytes;
+    }
+    if (!P.piece_mode) {
+        o[pos++] = 0x03;  // final empty fixed block: BFINAL=1, BTYPE=01, end-of-block code 0000000
+        o[pos++] = 0x00;
+    }
+    if (wb == 15) {
+        const uint32_t adler = P.unit_checks[2 * u];
+        o[pos++] = (uint8_t)(adler >> 24); o[pos++] = (uint8_t)(adler >> 16); o[pos++] = (uint8_t)(adler >> 8); o[pos++] = (uint8_t)adler;
+    } else if (wb > 15) {
+        const uint32_t crc = P.unit_checks[2 * u + 1];
+        const uint64_t in_len = P.seg_off[s1] - P.seg_off[s0];
+        for (int i = 0; i < 4; i++) o[pos++] = (uint8_t)(crc >> (8 * i));
+        for (int i = 0; i < 4; i++) o[pos++] = (uint8_t)((uint32_t)in_len >> (8 * i));  // ISIZE = length mod 2^32
+    }
+}
+
+// ------------------------------------------------------------------ K5b
+__global__ void __launch_bounds__(128) deflate_zero_kernel(DeflateParams P) {
+    const uint32_t slot = blockIdx.x * 128 + threadIdx.x;
+    if (slot >= P.n_slots) return;
+    uint32_t seg, b;
+    if (!slot_to_block(P, slot, seg, b) || P.st[seg].out_off == ~0ull) return;
+    const BlockPlan &bp = P.plans[slot];
+    uint8_t *o = P.out + P.st[seg].out_off;
+    const uint64_t e = block_end_bit(bp, bp.bit_off);
+    o[bp.bit_off >> 3] = 0;          // first byte of the block (may hold the tail of the previous block)
+    if (e & 7) o[e >> 3] = 0;        // last, partial byte of the block
+}
+
+// OR `v` into output byte `idx` (the byte is shared with a neighbouring block, so it was cleared by K5b)
+__device__ __forceinline__ void or_byte(uint8_t *o, uint64_t idx, uint32_t v) {
+    uintptr_t a = (uintptr_t)(o + idx);
+    atomicOr((unsigned int *)(a & ~(uintptr_t)3), v << (8 * (a & 3)));
+}
+
+// ------------------------------------------------------------------ K6
+#define CZK_EMIT_THREADS 256
+#define CZK_EMIT_WORDS (CZK_EMIT_THREADS * 48 / 32 + 4)
+__global__ void __launch_bounds__(CZK_EMIT_THREADS) deflate_emit_kernel(DeflateParams P) {
+    __shared__ uint32_t buf[CZK_EMIT_WORDS];
+    __shared__ uint32_t warp_sum[CZK_EMIT_THREADS / 32];
+    __shared__ uint32_t carry_bits_s, carry_val_s;
+    __shared__ uint32_t s_seg, s_b, s_ok;
+    if (threadIdx.x == 0) {
+        uint32_t sg, bb;
+        s_ok = slot_to_block(P, blockIdx.x, sg, bb) && P.st[sg].out_off != ~0ull;
+        s_seg = sg; s_b = bb;
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    const uint32_t seg = s_seg;
+    const BlockPlan &bp = P.plans[blockIdx.x];
+    uint8_t *o = P.out + P.st[seg].out_off;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (bp.btype == 0) {
+        // stored block(s): [3 zero bits + pad] [LEN NLEN] [bytes]; only the very first byte can be shared
+        const uint8_t *src = P.in + P.seg_off[seg] + bp.in_begin;
+        uint32_t left = bp.in_end - bp.in_begin;
+        uint64_t bits = bp.bit_off;
+        bool first = true;
+        do {
+            const uint32_t k = left > 65535 ? 65535 : left;
+            const uint64_t hb = (bits + 3 + 7) >> 3;  // byte index of LEN
+            if (tid == 0) {
+                // header bits are zeros: the shared first byte was cleared by K5b; later piece headers own their byte
+                if (!first) o[bits >> 3] = 0;
+                if (((bits + 2) >> 3) != (bits >> 3)) o[(bits + 2) >> 3] = 0;  // 3 header bits spill into the next byte
+                o[hb] = (uint8_t)k; o[hb + 1] = (uint8_t)(k >> 8); o[hb + 2] = (uint8_t)~k; o[hb + 3] = (uint8_t)(~k >> 8);
+            }
+            for (uint32_t i = tid; i < k; i += CZK_EMIT_THREADS) o[hb + 4 + i] = src[i];
+            src += k;
+            left -= k;
+            bits = (hb + 4 + k) * 8;
+            first = false;
+        } while (left);
+        return;
+    }
+    // ---- Huffman block: header words, then tokens (+ end-of-block), CZK_EMIT_THREADS items per round
+    const uint32_t *tok = P.match + seg_base(P, seg);
+    const uint32_t hdr_words = (bp.hdr_bits + 31) >> 5;
+    const uint32_t ntok = bp.tok_end - bp.tok_begin;
+    const uint32_t items = hdr_words + ntok + 1;  // + end-of-block
+    uint64_t gbit = bp.bit_off;                   // next free bit of the segment's output
+    if (tid == 0) { carry_bits_s = (uint32_t)(gbit & 7); carry_val_s = 0; }
+    for (uint32_t base = 0; base < items; base += CZK_EMIT_THREADS) {
+        for (uint32_t i = tid; i < CZK_EMIT_WORDS; i += CZK_EMIT_THREADS) buf[i] = 0;
+        const uint32_t it = base + tid;
+        uint64_t v = 0;
+        uint32_t n = 0;
+        if (it < hdr_words) {
+            v = bp.hdr[it];
+            n = it + 1 == hdr_words ? bp.hdr_bits - 32 * it : 32;
+        } else if (it < hdr_words + ntok) {
+            v = token_bits(tok[bp.tok_begin + it - hdr_words], bp, &n);
+        } else if (it == hdr_words + ntok) {
+            v = bp.lit_code[256];
+            n = bp.lit_len[256];
+        }
+        // exclusive scan of n over the CTA
+        uint32_t x = n;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(CZK_FULL, x, d);
+            if ((int)lane >= d) x += y;
+        }
+        if (lane == 31) warp_sum[wid] = x;
+        __syncthreads();
+        uint32_t wbase = 0, total = 0;
+        for (uint32_t w = 0; w < CZK_EMIT_THREADS / 32; w++) {
+            uint32_t sx = warp_sum[w];
+            if (w < wid) wbase += sx;
+            total += sx;
+        }
+        const uint32_t cb = carry_bits_s;      // bits (< 8) already pending in the first byte
+        uint32_t off = cb + wbase + x - n;     // bit offset inside buf
+        if (tid == 0 && cb) atomicOr(&buf[0], carry_val_s);
+        if (n) {
+            uint32_t w = off >> 5, sh = off & 31;
+            atomicOr(&buf[w], (uint32_t)(v << sh));
+            uint64_t hi = sh ? (v >> (32 - sh)) : (v >> 32);
+            if (sh + n > 32) atomicOr(&buf[w + 1], (uint32_t)hi);
+            if (sh + n > 64) atomicOr(&buf[w + 2], (uint32_t)(hi >> 32));
+        }
+        __syncthreads();
+        const uint32_t tbits = cb + total;               // valid bits in buf
+        const uint32_t full = tbits >> 3;                // complete bytes
+        const uint64_t byte0 = gbit >> 3;                // output byte of buf bit 0
+        const bool last_round = base + CZK_EMIT_THREADS >= items;
+        const bool first_shared = (base == 0) && (bp.bit_off & 7);  // byte 0 also holds bits of the previous block
+        for (uint32_t i = tid; i < full; i += CZK_EMIT_THREADS) {
+            uint32_t byte = (buf[i >> 2] >> (8 * (i & 3))) & 0xff;
+            if (i == 0 && first_shared) or_byte(o, byte0, byte); else o[byte0 + i] = (uint8_t)byte;
+        }
+        if (tid == 0) {
+            uint32_t rem = tbits & 7;
+            uint32_t rv = rem ? ((buf[full >> 2] >> (8 * (full & 3))) & 0xff) : 0;
+            if (last_round) {
+                if (rem) or_byte(o, byte0 + full, rv);  // last partial byte: shared with the next block / flush marker
+            } else {
+                carry_bits_s = rem;
+                carry_val_s = rv;
+            }
+        }
+        gbit += total;
+        __syncthreads();
+    }
+}
+
+}  // namespace czk

@@ -55,4 +55,9 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
                    const uint64_t *d_out_off, uint64_t *d_out_lens, int32_t *d_statuses, uint64_t *d_in_consumed,
                    uint32_t *d_checks, int window_bits, int segment_mode, int check_kind, void *d_ws, uint64_t ws_bytes);
 
+// batched inflate over host memory (host.cu); segment_mode / checks as in cz_inflate_segments_device
+int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint8_t *out, const uint64_t *out_off,
+                       uint64_t *out_lens, int32_t *statuses, uint64_t *in_consumed, int window_bits, int segment_mode,
+                       uint32_t *checks, uint32_t devices_mask);
+
 }  // namespace czh

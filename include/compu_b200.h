@@ -152,14 +152,17 @@ int cz_inflate_segments_device(void *cuda_stream, size_t n, const uint8_t *d_in,
                                void *d_workspace, uint64_t workspace_bytes);
 
 /* Deflate on device. Unit i = d_in[in_offsets[i]..in_offsets[i+1]) is compressed as ONE raw full-flush segment (no header,
-   no BFINAL, ends byte-aligned with 00 00 ff ff) into d_out[out_offsets[i]..]; d_out_lens[i] = bytes written,
-   d_checks[2i], d_checks[2i+1] = adler32, crc32 of the unit's input. Units must be <= cz_deflate_max_segment() bytes. */
+   no BFINAL, ends byte-aligned with 00 00 ff ff) into d_out[out_offsets[i]..]; d_out_lens[i] = bytes written (or needed, with
+   d_statuses[i] = CZ_ENCODE_NEED_OUTPUT, when the slot is smaller), d_checks[2i], d_checks[2i+1] = adler32, crc32 of the
+   unit's input (d_checks may be NULL). Units must be <= cz_deflate_max_segment() bytes; total_in_bytes =
+   in_offsets[n] - in_offsets[0] (the caller knows it; it sizes the workspace). */
 uint64_t cz_deflate_max_segment(void);
 uint64_t cz_deflate_segment_bound(uint64_t seg_len);
-uint64_t cz_deflate_workspace_bytes(size_t n_segments);
-int cz_deflate_segments_device(void *cuda_stream, size_t n, const uint8_t *d_in, const uint64_t *d_in_offsets, uint8_t *d_out,
-                               const uint64_t *d_out_offsets, uint64_t *d_out_lens, int32_t *d_statuses, uint32_t *d_checks,
-                               int level, int strategy, void *d_workspace, uint64_t workspace_bytes);
+uint64_t cz_deflate_workspace_bytes(size_t n_segments, uint64_t total_in_bytes);
+int cz_deflate_segments_device(void *cuda_stream, size_t n, const uint8_t *d_in, const uint64_t *d_in_offsets,
+                               uint64_t total_in_bytes, uint8_t *d_out, const uint64_t *d_out_offsets, uint64_t *d_out_lens,
+                               int32_t *d_statuses, uint32_t *d_checks, int level, int strategy, void *d_workspace,
+                               uint64_t workspace_bytes);
 
 /* Checksum combine over k segments on the host side of the gather (O(k) scalar work):
    folds per-segment {adler32, crc32, len} into whole-stream values. */

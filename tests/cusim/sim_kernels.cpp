@@ -3,6 +3,7 @@
 #include "../../compu_b200/csrc/inflate_kernel.cuh"
 #include "../../compu_b200/csrc/inflate_lane_kernel.cuh"
 #include "../../compu_b200/csrc/inflate_lc_kernel.cuh"
+#include "../../compu_b200/csrc/deflate_kernels.cuh"
 
 using namespace czk;
 
@@ -39,3 +40,44 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
 
 extern "C" uint32_t sim_crc32_combine(uint32_t a, uint32_t b, uint64_t len2) { return crc32_combine_u(a, b, len2); }
 extern "C" uint32_t sim_adler32_combine(uint32_t a, uint32_t b, uint64_t len2) { return adler32_combine_u(a, b, len2); }
+
+// The encoder's kernel chain in the order compu_b200/csrc/deflate.cu launches it, over host memory.
+// units: n_units with unit_seg[n_units+1] (null => unit == segment). window_bits/piece_mode as in DeflateParams.
+extern "C" int sim_deflate(size_t nseg, size_t n_units, const uint8_t *in, const uint64_t *seg_off, const uint32_t *unit_seg,
+                           uint8_t *out, const uint64_t *unit_out_off, uint64_t *unit_out_len, int32_t *unit_status,
+                           uint32_t *unit_checks, uint64_t *seg_out_bytes, int level, int strategy, int window_bits,
+                           int piece_mode, int packed, uint64_t *unit_out_pos, uint64_t *total_out, uint64_t seed) {
+    static CrcTables crc;
+    static bool crc_init = false;
+    if (!crc_init) { init_crc_tables(&crc); crc_init = true; }
+    const uint64_t in_bytes = seg_off[nseg] - seg_off[0];
+    const uint64_t n_slots = (in_bytes >> 14) + nseg + 1;
+    std::vector<SegState> st(nseg);
+    std::vector<uint16_t> prevd(in_bytes + 8);
+    std::vector<uint32_t> match(in_bytes + 8), blk_end(n_slots), freqs(n_slots * CZK_FREQ_STRIDE);
+    std::vector<BlockPlan> plans(n_slots);
+    DeflateParams P;
+    memset(&P, 0, sizeof P);
+    P.in = in; P.out = out; P.seg_off = seg_off; P.nseg = (uint32_t)nseg; P.n_units = (uint32_t)n_units; P.n_slots = (uint32_t)n_slots;
+    P.unit_seg = unit_seg; P.unit_out_off = unit_out_off; P.unit_out_pos = packed ? unit_out_pos : nullptr;
+    P.total_out = packed ? total_out : nullptr; P.unit_out_len = unit_out_len; P.unit_status = unit_status;
+    P.unit_checks = unit_checks; P.seg_out_bytes = seg_out_bytes; P.st = st.data(); P.prevd = prevd.data(); P.match = match.data();
+    P.blk_end = blk_end.data(); P.freqs = freqs.data(); P.plans = plans.data(); P.crc = &crc;
+    P.tune = deflate_tuning(level, strategy); P.window_bits = window_bits; P.level = level; P.piece_mode = piece_mode;
+    P.check_kind = unit_checks ? 3 : 0;
+    cusim::set_seed(seed);
+    const unsigned ns = P.nseg, nu = P.n_units, nsl = P.n_slots;
+    if (P.check_kind) cusim::launch((ns + 3) / 4, 128, 0, deflate_checksum_kernel, P);
+    if (!P.tune.level0 && !P.tune.huffman_only && !P.tune.rle_only) cusim::launch(ns < 3 ? ns : 3, 32, 0, deflate_chain_kernel, P);
+    cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_match_kernel, P, in_bytes);
+    cusim::launch((ns + 31) / 32, 32, 0, deflate_parse_kernel, P);
+    cusim::launch(nsl, 128, 0, deflate_hist_kernel, P);
+    cusim::launch((nsl + 31) / 32, 32, 0, deflate_plan_kernel, P);
+    cusim::launch((ns + 31) / 32, 32, 0, deflate_seg_layout_kernel, P);
+    cusim::launch((nu + 31) / 32, 32, 0, deflate_unit_size_kernel, P);
+    if (packed) cusim::launch(1, 1024, 0, deflate_scan_kernel, P);
+    cusim::launch((nu + 31) / 32, 32, 0, deflate_unit_frame_kernel, P);
+    cusim::launch((nsl + 127) / 128, 128, 0, deflate_zero_kernel, P);
+    cusim::launch(nsl, CZK_EMIT_THREADS, 0, deflate_emit_kernel, P);
+    return 0;
+}

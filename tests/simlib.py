@@ -46,3 +46,45 @@ def sim_inflate(streams, caps, window_bits, segment_mode=0, check_kind=0, D=4, g
     # nothing may be written past a slot's capacity
     assert (out[int(out_off[-1]):] == 0xEE).all()
     return outs, statuses, out_lens, consumed, checks
+
+
+def sim_deflate(units, seg_bytes=65536, level=6, strategy=0, window_bits=15, piece_mode=0, packed=0, caps=None, seed=1):
+    """Runs the encoder kernel chain on the emulator. Returns (streams, statuses, out_lens, checks, seg_sizes)."""
+    L = lib()
+    n = len(units)
+    inbuf, unit_off = pack(units)
+    seg_off, unit_seg = [], [0]
+    for u in range(n):
+        a, b = int(unit_off[u]), int(unit_off[u + 1])
+        while True:
+            seg_off.append(a)
+            a += min(seg_bytes, b - a)
+            if a >= b:
+                break
+        unit_seg.append(len(seg_off))
+    seg_off.append(int(unit_off[n]))
+    nseg = len(seg_off) - 1
+    seg_off = np.asarray(seg_off, dtype=np.uint64)
+    unit_seg = np.asarray(unit_seg, dtype=np.uint32)
+    if caps is None:
+        caps = [len(u) + len(u) // 2048 + 64 * (len(u) // seg_bytes + 1) + 32 for u in units]
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    out_off[1:] = np.cumsum(np.asarray(caps, dtype=np.uint64))
+    out = np.full(int(out_off[-1]) + 64, 0xEE, dtype=np.uint8)
+    out_len = np.zeros(n, dtype=np.uint64)
+    status = np.full(n, -99, dtype=np.int32)
+    checks = np.zeros(2 * n, dtype=np.uint32)
+    seg_sizes = np.zeros(nseg, dtype=np.uint64)
+    pos = np.zeros(n, dtype=np.uint64)
+    total = np.zeros(1, dtype=np.uint64)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    r = L.sim_deflate(ctypes.c_size_t(nseg), ctypes.c_size_t(n), p(inbuf), p(seg_off), p(unit_seg), p(out), p(out_off), p(out_len),
+                      p(status), p(checks), p(seg_sizes), level, strategy, window_bits, piece_mode, packed, p(pos), p(total),
+                      ctypes.c_uint64(seed))
+    assert r == 0
+    assert (out[int(out_off[-1]):] == 0xEE).all()
+    streams = []
+    for i in range(n):
+        o = int(pos[i]) if packed else int(out_off[i])
+        streams.append(bytes(out[o:o + int(out_len[i])]) if status[i] == 2 else b"")
+    return streams, status, out_len, checks, seg_sizes
