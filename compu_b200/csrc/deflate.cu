@@ -101,7 +101,10 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
         czk::deflate_chain_kernel<<<grid, 32, 0, st>>>(P);
     }
     czk::deflate_match_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
-    czk::deflate_parse_kernel<<<(nseg + 31) / 32, 32, 0, st>>>(P);
+    {
+        unsigned grid = nseg < (unsigned)ctx->sm_count * 16u ? nseg : (unsigned)ctx->sm_count * 16u;
+        czk::deflate_parse_kernel<<<grid, 32, 0, st>>>(P);
+    }
     czk::deflate_hist_kernel<<<nsl, 128, 0, st>>>(P);
     czk::deflate_plan_kernel<<<(nsl + 31) / 32, 32, 0, st>>>(P);
     czk::deflate_seg_layout_kernel<<<(nseg + 31) / 32, 32, 0, st>>>(P);

@@ -18,7 +18,8 @@
 //   K1 chains     warp per segment      prevd[]: 32 positions per step, __match_any_sync inside the step, a 16 KB
 //                                       shared-memory head table across steps (result == sequential insertion)
 //   K2 match      thread per position   best (length, distance) by walking the chain (deflate_core.cuh find_match)
-//   K3 parse      thread per segment    one-step-lazy parse into tokens, in place; cuts blocks of 16384 tokens
+//   K3 parse      warp per segment      one-step-lazy parse into tokens, in place (tile staged in shared memory, one
+//                                       lane walks the serial chain, all lanes emit); cuts blocks of 16384 tokens
 //   K4a histogram CTA per block         literal/length and distance symbol counts (shared-memory atomics)
 //   K4b plan      thread per block      length-limited Huffman codes, stored/fixed/dynamic choice, rendered header
 //   K5a layout    thread per segment    bit offset of every block, size of the segment
@@ -122,6 +123,10 @@ __global__ void __launch_bounds__(128) deflate_checksum_kernel(DeflateParams P) 
 
 // ------------------------------------------------------------------ K1
 // One warp per segment. Step k handles positions 32k..32k+31. Result == inserting the positions one by one.
+// head[h] holds the low 16 bits of the most recent position with hash h. To keep "age < 65536" true for every entry (so
+// that the 16-bit difference IS the distance) the table is swept every 16384 positions: entries 32768 or more behind are
+// re-stamped to exactly 32768 behind, which can never look recent before the next sweep. No global re-check is needed.
+#define CZK_CHAIN_SWEEP 16384u
 __global__ void __launch_bounds__(32) deflate_chain_kernel(DeflateParams P) {
     __shared__ uint16_t head[1u << CZK_HASH_BITS];
     const uint32_t lane = threadIdx.x;
@@ -130,13 +135,19 @@ __global__ void __launch_bounds__(32) deflate_chain_kernel(DeflateParams P) {
         const uint32_t n = seg_len(P, seg);
         uint16_t *pd = P.prevd + seg_base(P, seg);
         __syncwarp();
-        for (uint32_t i = lane; i < (1u << CZK_HASH_BITS); i += 32) head[i] = 0xffff;
+        for (uint32_t i = lane; i < (1u << CZK_HASH_BITS); i += 32) head[i] = 32768;  // "32768 behind position 0"
         __syncwarp();
+        uint32_t v_next = lane + 4 <= n ? load32u(s + lane) : 0u;  // the next step's bytes are always in flight
         for (uint32_t base = 0; base < n; base += 32) {
+            if (base && (base % CZK_CHAIN_SWEEP) == 0) {
+                for (uint32_t i = lane; i < (1u << CZK_HASH_BITS); i += 32)
+                    if (((base - (uint32_t)head[i]) & 0xffffu) >= CZK_WINDOW) head[i] = (uint16_t)((base - CZK_WINDOW) & 0xffffu);
+                __syncwarp();
+            }
             const uint32_t pos = base + lane;
             const bool valid = pos + 4 <= n;
-            uint32_t v = 0;
-            if (valid) v = load32(s + pos);
+            const uint32_t v = v_next;
+            v_next = pos + 32 + 4 <= n ? load32u(s + pos + 32) : 0u;
             // lanes without 4 bytes left get a private pseudo-hash so they never group with real ones
             const uint32_t h = valid ? hash4(v) : (0x10000u + lane);
             const uint32_t grp = __match_any_sync(CZK_FULL, h);
@@ -146,9 +157,7 @@ __global__ void __launch_bounds__(32) deflate_chain_kernel(DeflateParams P) {
                 if (lower) d = lane - (31u - (uint32_t)__clz((int)lower));  // nearest earlier lane with the same hash
                 else {
                     const uint32_t dd = (pos - (uint32_t)head[h]) & 0xffffu;
-                    // stale or never-written entries alias to some other position: keep the link only if that
-                    // position really has this hash (then it IS the most recent one, see deflate_model.cpp)
-                    if (dd >= 1 && dd < CZK_WINDOW && dd <= pos && hash4(load32(s + pos - dd)) == h) d = dd;
+                    if (dd >= 1 && dd < CZK_WINDOW && dd <= pos) d = dd;
                 }
             }
             if (pos < n) pd[pos] = (uint16_t)d;
@@ -183,15 +192,67 @@ __global__ void __launch_bounds__(256) deflate_match_kernel(DeflateParams P, uin
 }
 
 // ------------------------------------------------------------------ K3
+// One warp per segment. The parse itself is a serial chain (the next position depends on the match taken at this one), so
+// the warp stages a tile of positions in shared memory with coalesced loads, all lanes precompute "advance if a token
+// starts here" (match length, or 1 for a literal / a match deferred by the one-step lazy rule), ONE lane walks the tile
+// through shared memory marking token starts, and all lanes then emit the marked tokens with a popcount prefix.
+// Same decisions as parse_segment() in deflate_core.cuh (the sequential statement the tests compare against).
+#define CZK_PARSE_TILE 2048u
 __global__ void __launch_bounds__(32) deflate_parse_kernel(DeflateParams P) {
-    const uint32_t seg = blockIdx.x * 32 + threadIdx.x;
-    if (seg >= P.nseg) return;
-    const uint64_t base = seg_base(P, seg);
-    const uint32_t first = blk_first(P, seg), cap = blk_first(P, seg + 1) - first;
-    uint32_t nb = 0;
-    uint32_t nt = parse_segment(P.in + P.seg_off[seg], seg_len(P, seg), P.match + base, P.tune, P.blk_end + first, cap, &nb);
-    P.st[seg].ntok = nt;
-    P.st[seg].nblk = nb;
+    __shared__ uint32_t raw_s[CZK_PARSE_TILE + 1];
+    __shared__ uint16_t adv_s[CZK_PARSE_TILE];
+    __shared__ uint32_t vis_s[CZK_PARSE_TILE / 32];
+    const uint32_t lane = threadIdx.x;
+    for (uint32_t seg = blockIdx.x; seg < P.nseg; seg += gridDim.x) {
+        const uint64_t base = seg_base(P, seg);
+        const uint8_t *src = P.in + P.seg_off[seg];
+        const uint32_t n = seg_len(P, seg);
+        uint32_t *mt = P.match + base;
+        uint32_t *blk_end = P.blk_end + blk_first(P, seg);
+        uint32_t nt = 0;      // tokens emitted so far
+        uint32_t entry = 0;   // first token start inside the current tile (relative)
+        for (uint32_t t0 = 0; t0 < n; t0 += CZK_PARSE_TILE) {
+            const uint32_t T = n - t0 < CZK_PARSE_TILE ? n - t0 : CZK_PARSE_TILE;
+            __syncwarp();
+            for (uint32_t i = lane; i <= T; i += 32) raw_s[i] = t0 + i < n ? mt[t0 + i] : 0u;
+            if (lane < CZK_PARSE_TILE / 32) vis_s[lane] = 0;
+            for (uint32_t i = 32 + lane; i < CZK_PARSE_TILE / 32; i += 32) vis_s[i] = 0;
+            __syncwarp();
+            for (uint32_t i = lane; i < T; i += 32) {
+                const uint32_t len = raw_s[i] & 0x1ff;
+                const uint32_t nlen = (P.tune.lazy && t0 + i + 1 < n) ? (raw_s[i + 1] & 0x1ff) : 0;
+                adv_s[i] = (uint16_t)((len >= CZK_MIN_MATCH && !(nlen > len)) ? len : 1u);
+            }
+            __syncwarp();
+            uint32_t p = entry;
+            if (lane == 0) {
+                while (p < T) {
+                    vis_s[p >> 5] |= 1u << (p & 31);
+                    p += adv_s[p];
+                }
+            }
+            p = __shfl_sync(CZK_FULL, p, 0);
+            entry = p - T;
+            __syncwarp();
+            for (uint32_t w = 0; w * 32 < T; w++) {
+                const uint32_t bits = vis_s[w];
+                if (bits >> lane & 1u) {
+                    const uint32_t i = w * 32 + lane;
+                    const uint32_t k = nt + (uint32_t)__popc(bits & ((1u << lane) - 1u));
+                    const uint32_t a = adv_s[i];
+                    mt[k] = a == 1 ? (uint32_t)src[t0 + i] << 9 : raw_s[i];  // k <= t0 + i: never ahead of the tile being read
+                    if ((k + 1) % CZK_BLOCK_TOKENS == 0) blk_end[(k + 1) / CZK_BLOCK_TOKENS - 1] = t0 + i + a;
+                }
+                nt += (uint32_t)__popc(bits);
+            }
+        }
+        if (lane == 0) {
+            uint32_t nb = nt / CZK_BLOCK_TOKENS;
+            if (nt % CZK_BLOCK_TOKENS) blk_end[nb++] = n;  // last, partial block
+            P.st[seg].ntok = nt;
+            P.st[seg].nblk = nb;
+        }
+    }
 }
 
 // ------------------------------------------------------------------ K4a

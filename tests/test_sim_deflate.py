@@ -57,7 +57,9 @@ def test_sim_deflate_roundtrip_containers(alice, wbits):
 def test_sim_deflate_matches_sequential_model(alice):
     L = model_lib()
     rng = random.Random(11)
+    # the 230 000-byte unit crosses the 64 KiB wrap of the 16-bit head table and several sweeps
     units = [make_data(rng, k, n, alice) for k, n in [(0, 40000), (1, 3000), (2, 5000), (3, 9000), (4, 20000), (0, 17)]]
+    units.append((alice + alice[:80000])[:230000])
     streams, st, lens, _, seg_sizes = simlib.sim_deflate(units, seg_bytes=1 << 20, window_bits=-15, piece_mode=1)
     assert list(st) == [2] * len(units)
     for u, s in zip(units, streams):
