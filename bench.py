@@ -267,12 +267,12 @@ def main():
     d_out = torch.empty(U + 16, dtype=torch.uint8, device=dev)
     d_lens = torch.zeros(n, dtype=torch.int64, device=dev)
     d_stat = torch.zeros(n, dtype=torch.int32, device=dev)
-    ws_bytes = int(L.cz_inflate_workspace_bytes(n))
-    d_ws = torch.zeros(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
+    ws_bytes = int(L.cz_inflate_workspace_bytes(n, U))
+    d_ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
 
     def step():
         rc = L.cz_inflate_batch_device(sp, n, d_in.data_ptr(), d_in_off.data_ptr(), d_out.data_ptr(), d_out_off.data_ptr(),
-                                       d_lens.data_ptr(), d_stat.data_ptr(), None, 15, d_ws.data_ptr(), d_ws.numel())
+                                       U, d_lens.data_ptr(), d_stat.data_ptr(), None, 15, d_ws.data_ptr(), d_ws.numel())
         _lib.check(rc, "cz_inflate_batch_device")
 
     def barrier():
@@ -367,7 +367,7 @@ def main():
                        "inflate_cfg": os.environ.get("CZ_INFLATE_CFG", "default"),
                        "setup_s": {"synth_gpu": round(t_gen, 3), "zlib_compress_host": round(t_comp, 2)}},
             "e2e": e2e,
-            "gpu_launches": args.steps,  # one inflate kernel per step (plus a 256-byte memset node for the work counter)
+            "gpu_launches": 2 * args.steps,  # per step: inflate_tok_kernel + inflate_lz_kernel (plus a 256-byte memset node)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(U + C)},

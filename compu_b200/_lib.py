@@ -41,13 +41,14 @@ SIGNATURES = {
     "cz_deflate_segmented": (ci, [vp, u64, vp, u64, vp, ci, ci, ci, u64, u32, vp, u64, vp]),
     "cz_inflate_segmented": (ci, [vp, u64, vp, u64, vp, ci, u64, vp, u64, u32]),
     "cz_tune_inflate": (ci, [ci, ci]),
-    "cz_inflate_workspace_bytes": (u64, [sz]),
-    "cz_inflate_batch_device": (ci, [vp, sz, vp, vp, vp, vp, vp, vp, vp, ci, vp, u64]),
-    "cz_inflate_segments_device": (ci, [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp, u64]),
+    "cz_inflate_workspace_bytes": (u64, [sz, u64]),
+    "cz_inflate_batch_device": (ci, [vp, sz, vp, vp, vp, vp, u64, vp, vp, vp, ci, vp, u64]),
+    "cz_inflate_segments_device": (ci, [vp, sz, vp, vp, vp, vp, u64, vp, vp, vp, vp, u64]),
     "cz_deflate_max_segment": (u64, []),
     "cz_deflate_segment_bound": (u64, [u64]),
     "cz_deflate_workspace_bytes": (u64, [sz, u64]),
     "cz_deflate_segments_device": (ci, [vp, sz, vp, vp, u64, vp, vp, vp, vp, vp, ci, ci, vp, u64]),
+    "cz_partition_by_bytes": (ci, [sz, vp, ci, vp]),
     "cz_adler32_combine": (u32, [u32, u32, u64]),
     "cz_crc32_combine": (u32, [u32, u32, u64]),
     "cz_synth_model_bytes": (u64, []),

@@ -88,3 +88,12 @@ def inflate_segmented(stream, out_len, seg_index, window_bits=15, segment_bytes=
                                 len(idx) - 1, devices_mask)
     _lib.check(rc, "cz_inflate_segmented")
     return out[:got.value].tobytes()
+
+
+def partition_by_bytes(offsets, parts):
+    """Contiguous, byte-balanced shard cuts (the host-side partitioner of the batched entry points). No device needed."""
+    offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+    cuts = np.zeros(parts + 1, dtype=np.uint64)
+    rc = _lib.lib().cz_partition_by_bytes(len(offs) - 1, _p(offs), parts, _p(cuts))
+    _lib.check(rc, "cz_partition_by_bytes")
+    return [int(c) for c in cuts]

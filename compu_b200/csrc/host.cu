@@ -115,25 +115,47 @@ void PinBuf::release() {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// One device's share of a batched inflate: H2D, kernel, D2H on its own stream. Buffers are cached per thread+device.
+// One device's share of a batched inflate. The shard is cut into sub-batches (by output bytes) that are enqueued round
+// robin on a few streams: H2D of sub-batch k+1 overlaps the kernels of k and the D2H of k-1 (PCIe is full duplex), and the
+// kernels of different sub-batches overlap each other. Device buffers span the whole shard, so sub-batches never share
+// memory and need no ordering between them. Buffers are cached per thread+device.
+#define CZ_INFLATE_STREAMS 8
 struct InflateWork {
-    DevBuf in, out, meta;
-    cudaStream_t stream = nullptr;
+    DevBuf in, out, meta, ws;
+    PinBuf hres;  // per-unit results land here (pinned, so the D2H copies are truly asynchronous), then go to the caller's arrays
+    size_t res_n = 0, res_u0 = 0;
+    uint64_t *res_lens = nullptr, *res_cons = nullptr;
+    int32_t *res_stat = nullptr;
+    uint32_t *res_chk = nullptr;
+    cudaStream_t streams[CZ_INFLATE_STREAMS] = {};
+    cudaEvent_t meta_ready = nullptr;
     int dev = -1;
     bool init(int d) {
-        if (dev == d && stream) return true;
+        if (dev == d && streams[0]) return true;
         dev = d;
-        return CZ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (int i = 0; i < CZ_INFLATE_STREAMS; i++)
+            if (!CZ_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking))) return false;
+        return CZ_CUDA(cudaEventCreateWithFlags(&meta_ready, cudaEventDisableTiming));
     }
-    ~InflateWork() {
-        if (stream) cudaStreamDestroy(stream);
+    bool sync_all() {
+        bool ok = true;
+        for (int i = 0; i < CZ_INFLATE_STREAMS; i++)
+            if (streams[i] && !CZ_CUDA(cudaStreamSynchronize(streams[i]))) ok = false;
+        return ok;
     }
 };
 
-static inline uint32_t first_device(uint32_t mask) { return mask ? (uint32_t)__builtin_ctz(mask) : 0; }
+static uint64_t inflate_sub_batch_bytes() {
+    static uint64_t v = 0;
+    if (!v) {
+        v = 512ull << 20;
+        if (const char *e = getenv("CZ_INFLATE_SUB_MB")) { long m = atol(e); if (m >= 1 && m <= 65536) v = (uint64_t)m << 20; }
+    }
+    return v;
+}
 
 // Inflate units [u0,u1) of a packed host batch on device `dev`. Offsets are rebased so that the device buffers only
-// hold this shard. Synchronous from the caller's point of view (returns after the D2H copies have landed).
+// hold this shard. Everything is enqueued; the caller waits with InflateWork::sync_all().
 static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const uint8_t *in, const uint64_t *in_off, uint8_t *out,
                          const uint64_t *out_off, uint64_t *out_lens, int32_t *statuses, uint64_t *in_consumed,
                          int window_bits, int segment_mode, uint32_t *checks) {
@@ -143,27 +165,55 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
     const size_t n = u1 - u0;
     if (!n) return 0;
     const uint64_t ib = in_off[u0], ie = in_off[u1], ob = out_off[u0], oe = out_off[u1];
-    // meta layout: in_off[n+1] out_off[n+1] out_lens[n] consumed[n] statuses[n] checks[2n] workspace[256]
+    // sub-batches by output bytes
+    std::vector<size_t> cut;
+    cut.push_back(0);
+    {
+        const uint64_t lim = inflate_sub_batch_bytes();
+        size_t a = 0;
+        while (a < n) {
+            size_t e = a + 1;
+            while (e < n && out_off[u0 + e + 1] - out_off[u0 + a] <= lim) e++;
+            cut.push_back(e);
+            a = e;
+        }
+    }
+    const size_t nsub = cut.size() - 1;
+    // meta layout: in_off[n+1] out_off[n+1] out_lens[n] consumed[n] statuses[n] checks[2n]
     const size_t m_inoff = 0, m_outoff = m_inoff + 8 * (n + 1), m_lens = m_outoff + 8 * (n + 1), m_cons = m_lens + 8 * n,
-                 m_stat = m_cons + 8 * n, m_chk = align_up(m_stat + 4 * n, 8), m_ws = align_up(m_chk + 8 * n, 256),
-                 m_total = m_ws + 256;
-    if (!w.in.reserve(ie - ib + 16) || !w.out.reserve(oe - ob + 16) || !w.meta.reserve(m_total)) return CZ_E_MEM;
+                 m_stat = m_cons + 8 * n, m_chk = align_up(m_stat + 4 * n, 8), m_total = m_chk + 8 * n;
+    uint64_t ws_total = 0;
+    std::vector<uint64_t> ws_off(nsub + 1, 0);
+    for (size_t k = 0; k < nsub; k++) {
+        ws_total += align_up(inflate_workspace_bytes(cut[k + 1] - cut[k], out_off[u0 + cut[k + 1]] - out_off[u0 + cut[k]]), 256);
+        ws_off[k + 1] = ws_total;
+    }
+    if (!w.in.reserve(ie - ib + 16) || !w.out.reserve(oe - ob + 16) || !w.meta.reserve(m_total) || !w.ws.reserve(ws_total) ||
+        !w.hres.reserve(28 * n + 64)) return CZ_E_MEM;
+    w.res_n = n; w.res_u0 = u0;
+    w.res_lens = w.hres.as<uint64_t>(); w.res_cons = w.res_lens + n; w.res_stat = (int32_t *)(w.res_cons + n);
+    w.res_chk = (uint32_t *)(w.res_stat + n);
     std::vector<uint64_t> offs(2 * (n + 1));
     for (size_t i = 0; i <= n; i++) { offs[i] = in_off[u0 + i] - ib; offs[n + 1 + i] = out_off[u0 + i] - ob; }
     uint8_t *dm = w.meta.as<uint8_t>();
-    cudaStream_t st = w.stream;
-    if (!CZ_CUDA(cudaMemcpyAsync(dm, offs.data(), 16 * (n + 1), cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
-    if (ie > ib && !CZ_CUDA(cudaMemcpyAsync(w.in.p, in + ib, ie - ib, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
-    int r = launch_inflate(st, ctx, n, w.in.as<uint8_t>(), (const uint64_t *)(dm + m_inoff), w.out.as<uint8_t>(),
-                           (const uint64_t *)(dm + m_outoff), (uint64_t *)(dm + m_lens), (int32_t *)(dm + m_stat),
-                           (uint64_t *)(dm + m_cons), checks ? (uint32_t *)(dm + m_chk) : nullptr, window_bits, segment_mode,
-                           checks ? 3 : 0, dm + m_ws, 256);
-    if (r) return r;
-    if (oe > ob && !CZ_CUDA(cudaMemcpyAsync(out + ob, w.out.p, oe - ob, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
-    if (!CZ_CUDA(cudaMemcpyAsync(out_lens + u0, dm + m_lens, 8 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
-    if (!CZ_CUDA(cudaMemcpyAsync(statuses + u0, dm + m_stat, 4 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
-    if (in_consumed && !CZ_CUDA(cudaMemcpyAsync(in_consumed + u0, dm + m_cons, 8 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
-    if (checks && !CZ_CUDA(cudaMemcpyAsync(checks + 2 * u0, dm + m_chk, 8 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+    if (!CZ_CUDA(cudaMemcpyAsync(dm, offs.data(), 16 * (n + 1), cudaMemcpyHostToDevice, w.streams[0]))) return CZ_E_MEM;
+    if (!CZ_CUDA(cudaStreamSynchronize(w.streams[0]))) return CZ_E_MEM;  // `offs` is a stack-lifetime pageable buffer
+    for (size_t k = 0; k < nsub; k++) {
+        cudaStream_t st = w.streams[k % CZ_INFLATE_STREAMS];
+        const size_t a = cut[k], b = cut[k + 1], nk = b - a;
+        const uint64_t ia = offs[a], ibk = offs[b], oa = offs[n + 1 + a], obk = offs[n + 1 + b];
+        if (ibk > ia && !CZ_CUDA(cudaMemcpyAsync(w.in.as<uint8_t>() + ia, in + ib + ia, ibk - ia, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
+        int r = launch_inflate(st, ctx, nk, w.in.as<uint8_t>(), (const uint64_t *)(dm + m_inoff) + a, w.out.as<uint8_t>(),
+                               (const uint64_t *)(dm + m_outoff) + a, (uint64_t *)(dm + m_lens) + a, (int32_t *)(dm + m_stat) + a,
+                               (uint64_t *)(dm + m_cons) + a, checks ? (uint32_t *)(dm + m_chk) + 2 * a : nullptr, window_bits,
+                               segment_mode, checks ? 3 : 0, w.ws.as<uint8_t>() + ws_off[k], ws_off[k + 1] - ws_off[k], obk - oa);
+        if (r) return r;
+        if (obk > oa && !CZ_CUDA(cudaMemcpyAsync(out + ob + oa, w.out.as<uint8_t>() + oa, obk - oa, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+        if (!CZ_CUDA(cudaMemcpyAsync(w.res_lens + a, dm + m_lens + 8 * a, 8 * nk, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+        if (!CZ_CUDA(cudaMemcpyAsync(w.res_stat + a, dm + m_stat + 4 * a, 4 * nk, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+        if (in_consumed && !CZ_CUDA(cudaMemcpyAsync(w.res_cons + a, dm + m_cons + 8 * a, 8 * nk, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+        if (checks && !CZ_CUDA(cudaMemcpyAsync(w.res_chk + 2 * a, dm + m_chk + 8 * a, 8 * nk, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+    }
     return 0;
 }
 
@@ -202,9 +252,17 @@ int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint
         rc = inflate_shard(works[devs[k]], devs[k], cuts[k], cuts[k + 1], in, in_off, out, out_off, out_lens, statuses,
                            in_consumed, window_bits, segment_mode, checks);
     for (size_t k = 0; k < devs.size(); k++) {
-        if (!works[devs[k]].stream) continue;
+        if (!works[devs[k]].streams[0]) continue;
         cudaSetDevice(devs[k]);
-        if (!CZ_CUDA(cudaStreamSynchronize(works[devs[k]].stream)) && !rc) rc = CZ_E_MEM;
+        InflateWork &w = works[devs[k]];
+        if (!w.sync_all() && !rc) rc = CZ_E_MEM;
+        if (!rc && w.res_n) {
+            memcpy(out_lens + w.res_u0, w.res_lens, 8 * w.res_n);
+            memcpy(statuses + w.res_u0, w.res_stat, 4 * w.res_n);
+            if (in_consumed) memcpy(in_consumed + w.res_u0, w.res_cons, 8 * w.res_n);
+            if (checks) memcpy(checks + 2 * w.res_u0, w.res_chk, 8 * w.res_n);
+        }
+        w.res_n = 0;
     }
     cudaSetDevice(prev);
     return rc;
@@ -243,6 +301,14 @@ extern "C" const char *cz_describe_error(int32_t code) {
         case -6: return "incompatible version";
         default: return "";
     }
+}
+
+extern "C" int cz_partition_by_bytes(size_t n, const uint64_t *offsets, int parts, uint64_t *cuts) {
+    if (!offsets || !cuts || parts < 1) return CZ_E_STREAM;
+    std::vector<size_t> c;
+    split_by_bytes(n, offsets, parts, c);
+    for (int p = 0; p <= parts; p++) cuts[p] = c[p];
+    return 0;
 }
 
 extern "C" uint32_t cz_adler32_combine(uint32_t a, uint32_t b, uint64_t len2) { return czk::adler32_combine_u(a, b, len2); }

@@ -6,6 +6,7 @@
 #include "inflate_kernel.cuh"
 #include "inflate_lane_kernel.cuh"
 #include "inflate_lc_kernel.cuh"
+#include "inflate_two_phase.cuh"
 
 namespace czh {
 
@@ -77,11 +78,55 @@ static int launch_lc(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams &
     return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
 }
 
+// Two-phase path (default): phase A = lane-per-stream Huffman decode into tokens, phase B = warp-per-stream LZ77 resolution.
+// Workspace: [counter A 128 B | counter B 128 B] [TokMeta n] [token words total_out + 8 n]
+static inline uint64_t two_phase_meta_off() { return 256; }
+static inline uint64_t two_phase_tok_off(size_t n) { return align_up(256 + sizeof(czk::TokMeta) * (uint64_t)n, 256); }
+uint64_t inflate_workspace_bytes(size_t n, uint64_t total_out_bytes) {
+    return two_phase_tok_off(n) + 4 * (total_out_bytes + 8 * (uint64_t)n) + 256;
+}
+
+template <int WA, int WB>
+static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams &P, void *d_ws, uint64_t ws_bytes,
+                            uint64_t total_out_bytes) {
+    if (ws_bytes < inflate_workspace_bytes(P.n, total_out_bytes)) {
+        set_error("inflate workspace too small: %llu < %llu (see cz_inflate_workspace_bytes)", (unsigned long long)ws_bytes,
+                  (unsigned long long)inflate_workspace_bytes(P.n, total_out_bytes));
+        return CZ_E_MEM;
+    }
+    czk::TwoPhaseParams Q;
+    Q.base = P;
+    Q.counter_b = (unsigned long long *)((uint8_t *)d_ws + 128);
+    Q.meta = (czk::TokMeta *)((uint8_t *)d_ws + two_phase_meta_off());
+    Q.tok = (uint32_t *)((uint8_t *)d_ws + two_phase_tok_off(P.n));
+    auto ka = czk::inflate_tok_kernel<WA>;
+    auto kb = czk::inflate_lz_kernel<WB>;
+    const size_t smem = czk::inflate_tok_smem_bytes<WA>();
+    static bool configured[64] = {};
+    static int per_sm_a[64], per_sm_b[64];
+    const int d = ctx->dev & 63;
+    if (!configured[d]) {
+        if (!CZ_CUDA(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return CZ_E_MEM;
+        if (!CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a[d], ka, WA * 32, smem))) return CZ_E_MEM;
+        if (!CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b[d], kb, WB * 32, 0))) return CZ_E_MEM;
+        if (per_sm_a[d] < 1 || per_sm_b[d] < 1) { set_error("two-phase inflate kernels do not fit on an SM"); return CZ_E_MEM; }
+        configured[d] = true;
+    }
+    uint64_t ga = (P.n + 32 * WA - 1) / (32 * WA), gmax = (uint64_t)ctx->sm_count * per_sm_a[d];
+    if (ga > gmax) ga = gmax;
+    ka<<<(unsigned)ga, WA * 32, smem, st>>>(Q);
+    uint64_t gb = (P.n + WB - 1) / WB;
+    gmax = (uint64_t)ctx->sm_count * per_sm_b[d];
+    if (gb > gmax) gb = gmax;
+    kb<<<(unsigned)gb, WB * 32, 0, st>>>(Q);
+    return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
+}
+
 static InflateCfg g_cfg = {0, 0};
 
 static InflateCfg pick_cfg() {
     if (g_cfg.D == 0) {
-        InflateCfg c{-1, 14};  // lane-per-stream canonical-decode kernel, 14 warps (448 streams) per SM
+        InflateCfg c{-2, 14};  // two-phase: lane-per-stream token decode (14 warps per SM), then warp-per-stream LZ77
         if (const char *e = getenv("CZ_INFLATE_CFG")) {
             int d = 0, w = 0;
             if (sscanf(e, "%d,%d", &d, &w) == 2) { c.D = d; c.W = w; }
@@ -93,7 +138,8 @@ static InflateCfg pick_cfg() {
 
 int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out,
                    const uint64_t *d_out_off, uint64_t *d_out_lens, int32_t *d_statuses, uint64_t *d_in_consumed,
-                   uint32_t *d_checks, int window_bits, int segment_mode, int check_kind, void *d_ws, uint64_t ws_bytes) {
+                   uint32_t *d_checks, int window_bits, int segment_mode, int check_kind, void *d_ws, uint64_t ws_bytes,
+                   uint64_t total_out_bytes) {
     if (n == 0) return 0;
     if (n > 0xfffffff0u) { set_error("too many units in one launch"); return CZ_E_STREAM; }
     if (ws_bytes < 256 || !d_ws) { set_error("inflate workspace too small"); return CZ_E_MEM; }
@@ -111,6 +157,12 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
     CZ_CFG(1, 8); CZ_CFG(2, 8); CZ_CFG(4, 7); CZ_CFG(4, 4); CZ_CFG(8, 7); CZ_CFG(8, 4); CZ_CFG(8, 2); CZ_CFG(16, 3);
     CZ_CFG(16, 1); CZ_CFG(32, 1);
 #undef CZ_CFG
+    if (c.D == -2 && c.W == 14) return launch_two_phase<14, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes);
+    if (c.D == -2 && c.W == 12) return launch_two_phase<12, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes);
+    if (c.D == -2 && c.W == 10) return launch_two_phase<10, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes);
+    if (c.D == -2 && c.W == 7) return launch_two_phase<7, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes);
+    if (c.D == -2 && c.W == 4) return launch_two_phase<14, 4>(st, ctx, P, d_ws, ws_bytes, total_out_bytes);
+    if (c.D == -2 && c.W == 16) return launch_two_phase<14, 16>(st, ctx, P, d_ws, ws_bytes, total_out_bytes);
     // D = -1: lane-per-stream canonical-decode kernel with W warps per CTA
     if (c.D == -1 && c.W == 14) return launch_lc<14>(st, ctx, P);
     if (c.D == -1 && c.W == 12) return launch_lc<12>(st, ctx, P);
@@ -133,7 +185,7 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
 
 using namespace czh;
 
-extern "C" uint64_t cz_inflate_workspace_bytes(size_t) { return 256; }
+extern "C" uint64_t cz_inflate_workspace_bytes(size_t n, uint64_t total_out_bytes) { return inflate_workspace_bytes(n, total_out_bytes); }
 
 extern "C" int cz_tune_inflate(int slots_per_warp, int warps_per_cta) {
     g_cfg.D = slots_per_warp;
@@ -142,7 +194,7 @@ extern "C" int cz_tune_inflate(int slots_per_warp, int warps_per_cta) {
 }
 
 extern "C" int cz_inflate_batch_device(void *cuda_stream, size_t n, const uint8_t *d_in, const uint64_t *d_in_offsets,
-                                       uint8_t *d_out, const uint64_t *d_out_offsets, uint64_t *d_out_lens,
+                                       uint8_t *d_out, const uint64_t *d_out_offsets, uint64_t total_out_bytes, uint64_t *d_out_lens,
                                        int32_t *d_statuses, uint64_t *d_in_consumed, int window_bits, void *d_workspace,
                                        uint64_t workspace_bytes) {
     int dev = 0;
@@ -150,16 +202,16 @@ extern "C" int cz_inflate_batch_device(void *cuda_stream, size_t n, const uint8_
     DeviceCtx *ctx = device_ctx(dev);
     if (!ctx) return CZ_E_NO_DEVICE;
     return launch_inflate((cudaStream_t)cuda_stream, ctx, n, d_in, d_in_offsets, d_out, d_out_offsets, d_out_lens, d_statuses,
-                          d_in_consumed, nullptr, window_bits, 0, 0, d_workspace, workspace_bytes);
+                          d_in_consumed, nullptr, window_bits, 0, 0, d_workspace, workspace_bytes, total_out_bytes);
 }
 
 extern "C" int cz_inflate_segments_device(void *cuda_stream, size_t n, const uint8_t *d_in, const uint64_t *d_in_offsets,
-                                          uint8_t *d_out, const uint64_t *d_out_offsets, uint64_t *d_out_lens,
+                                          uint8_t *d_out, const uint64_t *d_out_offsets, uint64_t total_out_bytes, uint64_t *d_out_lens,
                                           int32_t *d_statuses, uint32_t *d_checks, void *d_workspace, uint64_t workspace_bytes) {
     int dev = 0;
     if (!CZ_CUDA(cudaGetDevice(&dev))) return CZ_E_NO_DEVICE;
     DeviceCtx *ctx = device_ctx(dev);
     if (!ctx) return CZ_E_NO_DEVICE;
     return launch_inflate((cudaStream_t)cuda_stream, ctx, n, d_in, d_in_offsets, d_out, d_out_offsets, d_out_lens, d_statuses,
-                          nullptr, d_checks, -15, 1, d_checks ? 3 : 0, d_workspace, workspace_bytes);
+                          nullptr, d_checks, -15, 1, d_checks ? 3 : 0, d_workspace, workspace_bytes, total_out_bytes);
 }

@@ -1,0 +1,436 @@
+// inflate_two_phase.cuh — batched inflate as TWO kernels (the default path).
+//
+// Why (profiles/r1_inflate_lc7_ncu.md): with one lane per stream doing everything, 65 536 streams are in flight at once
+// and their 32 KiB back-reference windows (2 GiB) thrash the 126 MB L2 — 13x the algorithmic DRAM traffic, every byte
+// store its own sector, the warps stalled on L2 misses. Huffman decoding is the only part that is inherently serial per
+// stream; LZ77 resolution is not. So the work is split where the dependency structure changes:
+//
+//   phase A  inflate_tok_kernel   one LANE per stream: container header, block headers, canonical Huffman decode (the 2x15
+//                                 code limits in registers, 448 B shared memory per stream, as inflate_lc_kernel.cuh).
+//                                 It produces no output bytes: it writes a compact TOKEN stream (sequential 4-byte
+//                                 stores) and validates everything that does not need the bytes (distances, capacity,
+//                                 block structure, ISIZE). Only sequential traffic: compressed in, tokens out.
+//   phase B  inflate_lz_kernel    one WARP per stream, few streams in flight (their windows fit L2): 32 tokens per step,
+//                                 a warp scan turns lengths into output positions, bytes are produced 32 at a time,
+//                                 sector-aligned, so every global store is one full 32-byte sector; back-references
+//                                 inside the round are resolved with shuffles. Adler-32 / CRC-32 are computed by the
+//                                 warp from the bytes it has just written and compared with the trailer values that
+//                                 phase A parsed.
+//
+// Token words (uint32):
+//   match    bit31 = 0           bits 0-8 length (1..258, may be cut by the output capacity), bits 9-24 distance (1..32768)
+//   literals bits 31-30 = 10     bits 24-25 count (1..3), bits 0-23 the bytes, first byte lowest
+//   stored   bits 31-30 = 11     three words: low 16 bits of word 0 = length, low 30 bits of words 1 and 2 = byte offset
+//                                of the run inside the unit's input (low, high)
+// Worst case one word per output byte (1-byte stored blocks are written as literal tokens), hence the 4 x capacity
+// token area per unit.
+//
+// Contract, status numbering and zlib's error order are those of inflate_kernel.cuh / inflate_lc_kernel.cuh.
+#pragma once
+#include "inflate_lc_kernel.cuh"
+
+namespace czk {
+
+struct TokMeta {
+    uint32_t ntok;       // token words written
+    int32_t status;      // preliminary status (final unless a checksum comparison is pending)
+    uint64_t out_len;    // bytes the tokens produce
+    uint32_t expect;     // trailer check value (Adler-32 or CRC-32) when status == FINISHED and wrap != 0
+    uint32_t wrap;       // 0 raw, 1 zlib (Adler-32), 2 gzip (CRC-32)
+};
+
+struct TwoPhaseParams {
+    InflateParams base;          // base.counter: phase A work counter
+    uint32_t *tok;               // token area: unit u starts at word tok_word_off(out_off[u] - out_off[0], u)
+    TokMeta *meta;               // n
+    unsigned long long *counter_b;  // phase B work counter, zero before launch
+};
+
+__host__ __device__ inline uint64_t tok_word_off(uint64_t out_off, uint64_t unit) { return out_off + 8 * unit; }
+
+#define CZK_TOK_LIT 0x80000000u
+#define CZK_TOK_STORED 0xC0000000u
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams Q) {
+    const InflateParams &P = Q.base;
+    CZ_DYNAMIC_SMEM(smem_raw);
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // layout: [length info 128 B] [per-warp scratch 256 B each] [WARPS*32 slots]
+    uint16_t *len_info = (uint16_t *)smem_raw;
+    uint32_t *wscr = (uint32_t *)(smem_raw + 128) + warp * 64;
+    LcSlot *slots = (LcSlot *)(smem_raw + 128 + WARPS * 256) + (size_t)warp * 32;
+    LcSlot &my = slots[lane];
+    if (threadIdx.x < 32) len_info[threadIdx.x] = (uint16_t)(threadIdx.x < 29 ? lc_len_info(threadIdx.x) : 0);
+    __syncthreads();
+
+    BitReader br;
+    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.total = 0;
+    uint32_t llim[15], dlim[15];
+#pragma unroll
+    for (int i = 0; i < 15; i++) { llim[i] = 0x10000u; dlim[i] = 0x10000u; }
+    int st = SS_IDLE;
+    uint32_t unit = 0;
+    const uint8_t *in_base = nullptr;
+    uint64_t in_len = 0;
+    uint64_t pos = 0, cap = 0;
+    uint32_t *tp = nullptr, *tp0 = nullptr;   // token write pointer / start
+    uint32_t lit = 0, nlit = 0;               // pending literal bytes (at most 2 between tokens)
+    int result = 0, wrap = 0;
+    uint32_t bfinal = 0, nlit_sym = 0, ndist_sym = 0, stored_len = 0, expect = 0;
+
+#define CZK_FLUSH_LIT() do { if (nlit) { *tp++ = CZK_TOK_LIT | (nlit << 24) | lit; lit = 0; nlit = 0; } } while (0)
+
+    for (;;) {
+        // ---- (1) fetch work
+        if (st == SS_IDLE) {
+            unsigned long long u = atomicAdd(P.counter, 1ull);
+            if (u >= P.n) st = SS_EXIT;
+            else {
+                unit = (uint32_t)u;
+                uint64_t i0 = P.in_off[unit], i1 = P.in_off[unit + 1], o0 = P.out_off[unit], o1 = P.out_off[unit + 1];
+                in_base = P.in + i0; in_len = i1 - i0;
+                cap = o1 - o0; pos = 0;
+                tp0 = tp = Q.tok + tok_word_off(o0 - P.out_off[0], unit);
+                lit = 0; nlit = 0; bfinal = 0; result = 0; expect = 0;
+                br.init(in_base, in_len);
+                st = SS_HEADER;
+            }
+        }
+        if (__all_sync(CZK_FULL, st == SS_EXIT)) break;
+
+        // ---- (2) container header
+        if (st == SS_HEADER) {
+            int r = 0;
+            if (P.segment_mode || P.window_bits < 0) wrap = 0;
+            else if (P.window_bits == 47) {
+                br.refill();
+                wrap = (in_len >= 2 && br.peek(16) == 0x8b1f) ? 2 : 1;
+            } else wrap = P.window_bits > 15 ? 2 : 1;
+            if (wrap == 1) r = parse_zlib_header(br);
+            else if (wrap == 2) r = parse_gzip_header(br);
+            if (r == 0) st = SS_BLOCK;
+            else { result = r == 100 ? ST_NEED_INPUT : r; st = SS_FINISH; }
+        }
+
+        // ---- (3) block header
+        if (st == SS_BLOCK) {
+            if (P.segment_mode && br.consumed() >= br.total) {
+                result = br.consumed() == br.total ? ST_FINISHED : ST_NEED_INPUT;
+                st = SS_TRAILER;
+            } else {
+                br.refill();
+                bfinal = br.get(1);
+                uint32_t btype = br.get(2);
+                if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; }
+                else if (btype == 0) {
+                    br.skip((uint32_t)((0 - br.consumed()) & 7));
+                    br.refill();
+                    uint32_t len = br.get(16);
+                    uint32_t nlen = br.get(16);
+                    if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; }
+                    else if ((len ^ 0xffffu) != nlen) { result = ST_E_DATA; st = SS_FINISH; }  // "invalid stored block lengths"
+                    else { stored_len = len; st = SS_STORED; }
+                } else if (btype == 1) {
+                    uint8_t *lens = lc_lens(my);
+                    for (uint32_t i = 0; i < 288; i++) lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
+                    for (uint32_t i = 0; i < 32; i++) lens[288 + i] = 5;
+                    nlit_sym = 288; ndist_sym = 32;
+                    st = SS_BUILD;
+                } else if (btype == 2) {
+                    int r = lc_parse_dynamic(br, my, nlit_sym, ndist_sym);
+                    if (r == 0) st = SS_BUILD;
+                    else { result = r == 100 ? ST_NEED_INPUT : r; st = SS_FINISH; }
+                } else { result = ST_E_DATA; st = SS_FINISH; }  // "invalid block type"
+            }
+        }
+
+        // ---- (4) warp-cooperative table construction, one slot at a time
+        {
+            uint32_t m = __ballot_sync(CZK_FULL, st == SS_BUILD);
+            while (m) {
+                int s = __ffs(m) - 1;
+                m &= m - 1;
+                uint32_t nl = __shfl_sync(CZK_FULL, nlit_sym, s), nd = __shfl_sync(CZK_FULL, ndist_sym, s);
+                __syncwarp();
+                int r = lc_build(slots[s], nl, nd, wscr, wscr + 16, lane, (uint32_t)s, llim, dlim);
+                if ((int)lane == s) {
+                    if (r) { result = ST_E_DATA; st = SS_FINISH; }
+                    else st = SS_DECODE;
+                }
+            }
+        }
+
+        // ---- (5) decode into tokens, lane-local, CZK_LC_BUDGET symbols per visit
+        if (st == SS_DECODE) {
+            int budget = CZK_LC_BUDGET;
+            while (budget-- > 0) {
+                br.refill();
+                uint32_t v = __brev((uint32_t)br.buf) >> 16;
+                uint32_t cl = lc_code_len(v, llim);
+                if (cl > 15) {  // no code matches (incomplete set) — or zero bits past a truncated input
+                    result = br.consumed() + 1 > br.total ? ST_NEED_INPUT : ST_E_DATA;
+                    st = SS_FINISH;
+                    break;
+                }
+                uint32_t info = my.lit_info[cl];
+                uint32_t idx = ((v >> (16 - cl)) + info) & 0xffffu;
+                uint32_t sym = my.lit_sorted[idx < 288 ? idx : 287] | (idx >= (info >> 16) ? 256u : 0u);
+                br.skip(cl);
+                if (sym < 256) {  // literal
+                    if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
+                    if (pos >= cap) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
+                    pos++;
+                    lit |= sym << (8 * nlit);
+                    if (++nlit == 3) { *tp++ = CZK_TOK_LIT | (3u << 24) | lit; lit = 0; nlit = 0; }
+                    continue;
+                }
+                if (sym == 256) {  // end of block
+                    if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
+                    if (bfinal) { result = ST_FINISHED; st = SS_TRAILER; } else st = SS_BLOCK;
+                    break;
+                }
+                if (sym > 285) {  // 286/287 only exist in the fixed code and are invalid
+                    result = br.overrun() ? ST_NEED_INPUT : ST_E_DATA;
+                    st = SS_FINISH;
+                    break;
+                }
+                uint32_t li = len_info[sym - 257];
+                uint32_t eb = li >> 9;
+                uint32_t len = (li & 0x1ff) + br.peek(eb);
+                br.skip(eb);
+                br.refill();
+                v = __brev((uint32_t)br.buf) >> 16;
+                uint32_t dcl = lc_code_len(v, dlim);
+                if (dcl > 15) {
+                    result = br.consumed() + 1 > br.total ? ST_NEED_INPUT : ST_E_DATA;
+                    st = SS_FINISH;
+                    break;
+                }
+                uint32_t dsym = my.dist_sorted[((v >> (16 - dcl)) + my.dist_base[dcl]) & 31];
+                br.skip(dcl);
+                if (dsym > 29) { result = br.overrun() ? ST_NEED_INPUT : ST_E_DATA; st = SS_FINISH; break; }
+                uint32_t deb = dsym < 2 ? 0 : (dsym >> 1) - 1;
+                uint32_t dist = ((dsym < 2 ? dsym : 2 + (dsym & 1)) << deb) + 1 + br.peek(deb);
+                br.skip(deb);
+                if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
+                // zlib order (inflate.c MATCH): output space first, then "invalid distance too far back"
+                if (pos >= cap) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
+                if ((uint64_t)dist > pos) { result = ST_E_DATA; st = SS_FINISH; break; }
+                uint32_t n = len;
+                if (pos + n > cap) n = (uint32_t)(cap - pos);
+                CZK_FLUSH_LIT();
+                *tp++ = n | (dist << 9);
+                pos += n;
+                if (n < len) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
+            }
+        }
+
+        // ---- (6) stored blocks: short runs become literal tokens, longer ones a reference into the input
+        if (st == SS_STORED) {
+            const uint64_t ipos = br.consumed() >> 3;
+            int err = -1;
+            uint32_t n = stored_len;
+            if (ipos + n > in_len) { n = (uint32_t)(in_len - ipos); err = ST_NEED_INPUT; }
+            if (pos + n > cap) { n = (uint32_t)(cap - pos); err = ST_NEED_OUTPUT; }
+            if (n > 8) {
+                CZK_FLUSH_LIT();
+                *tp++ = CZK_TOK_STORED | n;
+                *tp++ = CZK_TOK_STORED | (uint32_t)(ipos & 0x3fffffffu);
+                *tp++ = CZK_TOK_STORED | (uint32_t)(ipos >> 30);
+            } else {
+                for (uint32_t k = 0; k < n; k++) {
+                    lit |= (uint32_t)in_base[ipos + k] << (8 * nlit);
+                    if (++nlit == 3) { *tp++ = CZK_TOK_LIT | (3u << 24) | lit; lit = 0; nlit = 0; }
+                }
+            }
+            pos += n;
+            br.seek(ipos + n);
+            if (err >= 0) { result = err; st = SS_FINISH; }
+            else if (bfinal) { result = ST_FINISHED; st = SS_TRAILER; }
+            else st = SS_BLOCK;
+        }
+
+        // ---- (7) trailer: the check value is compared by phase B, the length check happens here
+        if (st == SS_TRAILER) {
+            if (!P.segment_mode && result == ST_FINISHED) {
+                br.skip((uint32_t)((0 - br.consumed()) & 7));
+                if (wrap == 1) {
+                    uint32_t t = 0;
+                    for (int i = 0; i < 4; i++) t = (t << 8) | br.get_byte();
+                    if (br.overrun()) result = ST_NEED_INPUT;
+                    expect = t;
+                } else if (wrap == 2) {
+                    uint32_t t = 0, isz = 0;
+                    for (int i = 0; i < 4; i++) t |= br.get_byte() << (8 * i);
+                    for (int i = 0; i < 4; i++) isz |= br.get_byte() << (8 * i);
+                    if (br.overrun()) result = ST_NEED_INPUT;
+                    else if (isz != (uint32_t)pos) result = ST_E_DATA;  // "incorrect length check" (the data check comes first in
+                    expect = t;                                         //  zlib, but both map to the same code)
+                }
+            }
+            st = SS_FINISH;
+        }
+
+        // ---- (8) hand over to phase B
+        if (st == SS_FINISH) {
+            CZK_FLUSH_LIT();
+            TokMeta m;
+            m.ntok = (uint32_t)(tp - tp0);
+            m.status = result;
+            m.out_len = pos;
+            m.expect = expect;
+            m.wrap = (uint32_t)wrap;
+            Q.meta[unit] = m;
+            if (P.in_consumed) {
+                uint64_t c = (br.consumed() + 7) >> 3;
+                P.in_consumed[unit] = c < in_len ? c : in_len;
+            }
+            st = SS_IDLE;
+        }
+    }
+#undef CZK_FLUSH_LIT
+}
+
+template <int WARPS>
+constexpr size_t inflate_tok_smem_bytes() { return 128 + WARPS * 256 + sizeof(LcSlot) * 32 * (size_t)WARPS; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Phase B: one warp per unit.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) inflate_lz_kernel(TwoPhaseParams Q) {
+    const InflateParams &P = Q.base;
+    __shared__ uint32_t crc_tab[256 + 34];
+    const uint32_t lane = threadIdx.x & 31;
+    if (P.crc)
+        for (uint32_t i = threadIdx.x; i < 256 + 34; i += WARPS * 32) crc_tab[i] = i < 256 ? P.crc->table[i] : P.crc->pow128[i - 256];
+    __syncthreads();
+    const uint32_t *crc_pow = crc_tab + 256;
+
+    for (;;) {
+        unsigned long long u64 = 0;
+        if (lane == 0) u64 = atomicAdd(Q.counter_b, 1ull);
+        u64 = __shfl_sync(CZK_FULL, u64, 0);
+        if (u64 >= P.n) break;
+        const uint32_t unit = (uint32_t)u64;
+        const TokMeta m = Q.meta[unit];
+        const uint64_t o0 = P.out_off[unit];
+        uint8_t *ob = P.out + o0;
+        const uint8_t *ib = P.in + P.in_off[unit];
+        const uint32_t *tok = Q.tok + tok_word_off(o0 - P.out_off[0], unit);
+        const uint32_t ntok = m.ntok;
+        const bool want_adler = P.segment_mode ? (P.check_kind & 1) : m.wrap == 1;
+        const bool want_crc = P.segment_mode ? (P.check_kind & 2) : m.wrap == 2;
+        uint64_t opos = 0, ck_pos = 0;
+        uint32_t adler = 1, crc = 0;
+        uint32_t ti = 0;
+        while (ti < ntok) {
+            const uint32_t t_raw = ti + lane < ntok ? tok[ti + lane] : CZK_TOK_STORED;  // past the end: acts as a stop mark
+            const uint32_t stopm = __ballot_sync(CZK_FULL, (t_raw >> 30) == 3u);
+            const uint32_t nt = stopm ? (uint32_t)__ffs(stopm) - 1u : 32u;  // ordinary tokens before the first stored mark
+            if (nt) {
+                const uint32_t t = lane < nt ? t_raw : 0u;
+                const uint32_t tl = (t >> 31) ? ((t >> 24) & 3u) : (t & 0x1ffu);
+                // exclusive scan of lengths
+                uint32_t pos = tl;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t v = __shfl_up_sync(CZK_FULL, pos, d);
+                    if ((int)lane >= d) pos += v;
+                }
+                const uint32_t total = __shfl_sync(CZK_FULL, pos, 31);
+                pos -= tl;
+                const uint64_t a0 = (uint64_t)(uintptr_t)ob + opos;   // absolute address of batch byte 0
+                int rel = -(int)(a0 & 31);                             // batch-relative index of this round's lane 0
+                uint32_t cnt_before = 0;
+                uint8_t *obp = ob + opos;
+                for (; rel < (int)total; rel += 32) {
+                    // which tokens start inside this round? (every token covers at least one byte)
+                    uint32_t bit = (lane < nt && (int)pos >= rel && (int)pos < rel + 32) ? 1u << ((int)pos - rel) : 0u;
+                    uint32_t S = __reduce_or_sync(CZK_FULL, bit);
+                    int j = rel + (int)lane;
+                    bool active = j >= 0 && j < (int)total;
+                    // lane holding the token that covers byte j
+                    int src_lane = (int)cnt_before + __popc(S & (0xffffffffu >> (31 - lane))) - 1;
+                    cnt_before += __popc(S);
+                    uint32_t val = 0;
+                    bool need = false;
+                    int srcl = 0;
+                    uint32_t tk = __shfl_sync(CZK_FULL, t, src_lane & 31);
+                    uint32_t tpp = __shfl_sync(CZK_FULL, pos, src_lane & 31);
+                    if (active) {
+                        uint32_t off = (uint32_t)j - tpp;
+                        if (tk >> 31) val = (tk >> (8 * off)) & 0xff;
+                        else {
+                            uint32_t dist = (tk >> 9) & 0xffffu;
+                            if (off >= dist) off %= dist;
+                            int src = (int)tpp - (int)dist + (int)off;  // batch-relative source index (< tpp)
+                            int lo2 = rel > 0 ? rel : 0;
+                            if (src >= lo2) { need = true; srcl = src - rel; }
+                            else val = obp[src];                        // bytes of earlier rounds / batches
+                        }
+                    }
+                    uint32_t pend = __ballot_sync(CZK_FULL, need);
+                    while (pend) {
+                        uint32_t v = __shfl_sync(CZK_FULL, val, srcl);
+                        bool src_ready = !((pend >> srcl) & 1u);
+                        if (need && src_ready) { val = v; need = false; }
+                        pend = __ballot_sync(CZK_FULL, need);
+                    }
+                    if (active) obp[j] = (uint8_t)val;
+                    __syncwarp();
+                }
+                opos += total;
+                ti += nt;
+            }
+            if (nt < 32 && ti < ntok) {
+                // a stored run: three marked words starting at ti
+                const uint32_t w0 = tok[ti], w1 = tok[ti + 1], w2 = tok[ti + 2];
+                const uint32_t n = w0 & 0xffffu;
+                const uint64_t ipos = (uint64_t)(w1 & 0x3fffffffu) | ((uint64_t)(w2 & 0x3fffffffu) << 30);
+                for (uint32_t k = lane; k < n; k += 32) ob[opos + k] = ib[ipos + k];
+                __syncwarp();
+                opos += n;
+                ti += 3;
+            }
+            // ---- checksums over freshly written output (L1/L2 hits), in pieces
+            if ((want_adler || want_crc) && (opos - ck_pos >= 8192 || ti >= ntok)) {
+                uint64_t to = opos;
+                if (ti < ntok) to = ck_pos + ((to - ck_pos) & ~(uint64_t)127);  // keep CRC pieces at 128 B until the end
+                if (want_adler) {
+                    for (uint64_t p = ck_pos; p < to; p += 8192) {
+                        uint32_t n = (uint32_t)(to - p < 8192 ? to - p : 8192);
+                        adler = warp_adler32(adler, ob + p, n, lane);
+                    }
+                }
+                if (want_crc) {
+                    uint64_t p = ck_pos;
+                    while (to - p >= 128) {
+                        uint32_t q = (uint32_t)((to - p) >> 7);
+                        if (q > 32) q = 32;
+                        crc = warp_crc32_pieces(crc, ob + p, q, crc_tab, crc_pow, lane);
+                        p += (uint64_t)q * 128;
+                    }
+                    if (p < to) {
+                        uint32_t c2 = 0;
+                        if (lane == 0) c2 = crc32_serial(crc, ob + p, (uint32_t)(to - p), crc_tab);
+                        crc = __shfl_sync(CZK_FULL, c2, 0);
+                    }
+                }
+                ck_pos = to;
+            }
+        }
+        if (lane == 0) {
+            int status = m.status;
+            if (status == ST_FINISHED && !P.segment_mode) {
+                if (m.wrap == 1 && m.expect != adler) status = ST_E_DATA;  // "incorrect data check"
+                if (m.wrap == 2 && m.expect != crc) status = ST_E_DATA;
+            }
+            P.out_lens[unit] = opos;
+            P.statuses[unit] = status;
+            if (P.checks) { P.checks[2 * unit] = adler; P.checks[2 * unit + 1] = crc; }
+        }
+    }
+}
+
+}  // namespace czk

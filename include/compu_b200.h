@@ -134,22 +134,23 @@ int cz_inflate_segmented(const uint8_t *in, uint64_t len, uint8_t *out, uint64_t
 /* Same contracts, all pointers are device pointers on the CURRENT CUDA device, work is enqueued on `cuda_stream`
    (a cudaStream_t passed as void*) and NOT synchronised. These are what bench.py times for the roofline figure. */
 
-/* Tuning knob: decoder slots per warp (streams decoded concurrently by one warp) and warps per CTA of the inflate kernel.
-   Only instantiated pairs are accepted at launch (see compu_b200/csrc/inflate.cu); default from CZ_INFLATE_CFG or 8,7. */
+/* Tuning knob (experiments): selects an inflate kernel variant; see compu_b200/csrc/inflate.cu. Default from CZ_INFLATE_CFG
+   or -2,14 (two-phase: lane-per-stream token decode with 14 warps per SM, then warp-per-stream LZ77 resolution). */
 int cz_tune_inflate(int slots_per_warp, int warps_per_cta);
 
-/* Scratch bytes cz_inflate_batch_device needs for n streams (0 is possible). */
-uint64_t cz_inflate_workspace_bytes(size_t n);
+/* Scratch bytes cz_inflate_batch_device needs for n streams whose output slots total total_out_bytes
+   (= d_out_offsets[n] - d_out_offsets[0]; the token area of the two-phase kernel is 4 bytes per output byte). */
+uint64_t cz_inflate_workspace_bytes(size_t n, uint64_t total_out_bytes);
 int cz_inflate_batch_device(void *cuda_stream, size_t n, const uint8_t *d_in, const uint64_t *d_in_offsets, uint8_t *d_out,
-                            const uint64_t *d_out_offsets, uint64_t *d_out_lens, int32_t *d_statuses,
+                            const uint64_t *d_out_offsets, uint64_t total_out_bytes, uint64_t *d_out_lens, int32_t *d_statuses,
                             uint64_t *d_in_consumed, int window_bits, void *d_workspace, uint64_t workspace_bytes);
 
 /* Raw-segment form used for segment-parallel inflate: every unit is a raw-deflate fragment that never sets BFINAL and
    ends exactly at the end of its input (what a full-flush segment is); finishing at end-of-input is success.
    d_checks (optional) receives per unit {adler32, crc32} of the produced bytes as two uint32. */
 int cz_inflate_segments_device(void *cuda_stream, size_t n, const uint8_t *d_in, const uint64_t *d_in_offsets, uint8_t *d_out,
-                               const uint64_t *d_out_offsets, uint64_t *d_out_lens, int32_t *d_statuses, uint32_t *d_checks,
-                               void *d_workspace, uint64_t workspace_bytes);
+                               const uint64_t *d_out_offsets, uint64_t total_out_bytes, uint64_t *d_out_lens,
+                               int32_t *d_statuses, uint32_t *d_checks, void *d_workspace, uint64_t workspace_bytes);
 
 /* Deflate on device. Unit i = d_in[in_offsets[i]..in_offsets[i+1]) is compressed as ONE raw full-flush segment (no header,
    no BFINAL, ends byte-aligned with 00 00 ff ff) into d_out[out_offsets[i]..]; d_out_lens[i] = bytes written (or needed, with
@@ -168,6 +169,11 @@ int cz_deflate_segments_device(void *cuda_stream, size_t n, const uint8_t *d_in,
    folds per-segment {adler32, crc32, len} into whole-stream values. */
 uint32_t cz_adler32_combine(uint32_t adler1, uint32_t adler2, uint64_t len2);
 uint32_t cz_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
+
+/* The multi-GPU partitioner used by the batched entry points: cuts n packed units (offsets[n+1]) into `parts`
+   contiguous ranges balanced by bytes, no collective. cuts[parts+1] receives unit indices, cuts[0] = 0, cuts[parts] = n.
+   Pure host arithmetic (no device needed), exported so that callers sharding over processes use the same cuts. */
+int cz_partition_by_bytes(size_t n, const uint64_t *offsets, int parts, uint64_t *cuts);
 
 /* Synthetic data with controlled entropy, generated on the current device. kind: 0 Markov text (needs
    d_model from cz_synth_model_bytes/cz_synth_build_model), 1 repeated-substring Zipf, 2 near-random mix, 3 round-robin

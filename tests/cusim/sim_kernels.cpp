@@ -3,6 +3,7 @@
 #include "../../compu_b200/csrc/inflate_kernel.cuh"
 #include "../../compu_b200/csrc/inflate_lane_kernel.cuh"
 #include "../../compu_b200/csrc/inflate_lc_kernel.cuh"
+#include "../../compu_b200/csrc/inflate_two_phase.cuh"
 #include "../../compu_b200/csrc/deflate_kernels.cuh"
 
 using namespace czk;
@@ -31,6 +32,18 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
         case 8: run_inflate<8, 1>(P, grid); break;
         case 32: run_inflate<32, 1>(P, grid); break;
         case -1: cusim::launch(grid, 2 * 32, inflate_lc_smem_bytes<2>(), inflate_lc_kernel<2>, P); break;
+        case -2: {
+            const uint64_t total_out = out_off[n] - out_off[0];
+            std::vector<uint32_t> tok(total_out + 8 * n + 64, 0xDEADBEEFu);
+            std::vector<TokMeta> meta(n);
+            unsigned long long counter_b = 0;
+            TwoPhaseParams Q;
+            Q.base = P; Q.tok = tok.data(); Q.meta = meta.data(); Q.counter_b = &counter_b;
+            cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2>, Q);
+            cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2>, Q);
+            for (size_t i = total_out + 8 * n; i < tok.size(); i++) if (tok[i] != 0xDEADBEEFu) return -2;  // token area overrun
+            break;
+        }
         case -9: cusim::launch(grid, 2 * 32, inflate_lane_smem_bytes<9, 8, 2>(), inflate_lane_kernel<9, 8, 2>, P); break;
         case -8: cusim::launch(grid, 1 * 32, inflate_lane_smem_bytes<8, 7, 1>(), inflate_lane_kernel<8, 7, 1>, P); break;
         default: return -1;

@@ -230,12 +230,13 @@ def test_device_api_segments(alice):
     d_chk2 = torch.zeros(2 * n, dtype=torch.int32, device=dev)
     comp_off = np.zeros(n + 1, dtype=np.int64)
     # segments sit in their slots, so inflate them slot by slot: in_off = slot start .. slot start + len
-    d_ws2 = torch.zeros(256, dtype=torch.uint8, device=dev)
+    ws2 = int(L.cz_inflate_workspace_bytes(1, max(len(x) for x in segs)))
+    d_ws2 = torch.zeros(ws2, dtype=torch.uint8, device=dev)
     for i in range(n):
         io = torch.tensor([out_off[i], out_off[i] + int(d_lens[i])], dtype=torch.int64, device=dev)
         oo = torch.tensor([in_off[i], in_off[i + 1]], dtype=torch.int64, device=dev)
-        rc = L.cz_inflate_segments_device(sp, 1, d_out.data_ptr(), io.data_ptr(), d_back.data_ptr(), oo.data_ptr(),
-                                          d_lens2[i:].data_ptr(), d_st2[i:].data_ptr(), d_chk2[2 * i:].data_ptr(), d_ws2.data_ptr(), 256)
+        rc = L.cz_inflate_segments_device(sp, 1, d_out.data_ptr(), io.data_ptr(), d_back.data_ptr(), oo.data_ptr(), len(segs[i]),
+                                          d_lens2[i:].data_ptr(), d_st2[i:].data_ptr(), d_chk2[2 * i:].data_ptr(), d_ws2.data_ptr(), ws2)
         _lib.check(rc, "cz_inflate_segments_device")
     torch.cuda.synchronize()
     assert d_st2.tolist() == [2] * n

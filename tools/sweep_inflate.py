@@ -50,7 +50,8 @@ def main():
     d_out = torch.empty(U + 16, dtype=torch.uint8, device=dev)
     d_lens = torch.zeros(n, dtype=torch.int64, device=dev)
     d_stat = torch.zeros(n, dtype=torch.int32, device=dev)
-    d_ws = torch.zeros(256, dtype=torch.uint8, device=dev)
+    ws_bytes = int(L.cz_inflate_workspace_bytes(n, U))
+    d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     print(json.dumps({"streams": n, "kind": args.kind, "ratio": U / C, "host_compress_s": t_comp, "cores": os.cpu_count()}))
     for cfg in args.cfgs.split(";"):
         D, W = [int(x) for x in cfg.split(",")]
@@ -58,7 +59,7 @@ def main():
 
         def step():
             rc = L.cz_inflate_batch_device(sp, n, d_in.data_ptr(), d_in_off.data_ptr(), d_out.data_ptr(), d_out_off.data_ptr(),
-                                           d_lens.data_ptr(), d_stat.data_ptr(), None, 15, d_ws.data_ptr(), 256)
+                                           U, d_lens.data_ptr(), d_stat.data_ptr(), None, 15, d_ws.data_ptr(), ws_bytes)
             _lib.check(rc, "inflate")
         d_out.zero_()
         step()
