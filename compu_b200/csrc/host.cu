@@ -179,13 +179,27 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
         }
     }
     const size_t nsub = cut.size() - 1;
-    // meta layout: in_off[n+1] out_off[n+1] out_lens[n] consumed[n] statuses[n] checks[2n]
+    // big units (megabytes in one stream) go to the warp-per-stream kernel, the rest to the two-phase path
+    const uint64_t big_in = 192u << 10, big_out = 1u << 20;
+    std::vector<uint32_t> ids;  // per sub-batch: [small ids..., big ids...], relative to the sub-batch's first unit
+    std::vector<size_t> n_small(nsub, 0), n_big(nsub, 0), ids_at(nsub + 1, 0);
+    bool any_big = false;
+    for (size_t k = 0; k < nsub; k++) {
+        ids_at[k] = ids.size();
+        for (int pass = 0; pass < 2; pass++)
+            for (size_t i = cut[k]; i < cut[k + 1]; i++) {
+                const bool big = in_off[u0 + i + 1] - in_off[u0 + i] > big_in || out_off[u0 + i + 1] - out_off[u0 + i] > big_out;
+                if ((int)big == pass) { ids.push_back((uint32_t)(i - cut[k])); (big ? n_big[k] : n_small[k])++; any_big |= big; }
+            }
+    }
+    ids_at[nsub] = ids.size();
+    // meta layout: in_off[n+1] out_off[n+1] out_lens[n] consumed[n] statuses[n] checks[2n] ids[n]
     const size_t m_inoff = 0, m_outoff = m_inoff + 8 * (n + 1), m_lens = m_outoff + 8 * (n + 1), m_cons = m_lens + 8 * n,
-                 m_stat = m_cons + 8 * n, m_chk = align_up(m_stat + 4 * n, 8), m_total = m_chk + 8 * n;
+                 m_stat = m_cons + 8 * n, m_chk = align_up(m_stat + 4 * n, 8), m_ids = m_chk + 8 * n, m_total = m_ids + 4 * n;
     uint64_t ws_total = 0;
     std::vector<uint64_t> ws_off(nsub + 1, 0);
     for (size_t k = 0; k < nsub; k++) {
-        ws_total += align_up(inflate_workspace_bytes(cut[k + 1] - cut[k], out_off[u0 + cut[k + 1]] - out_off[u0 + cut[k]]), 256);
+        ws_total += align_up(inflate_workspace_bytes(cut[k + 1] - cut[k], out_off[u0 + cut[k + 1]] - out_off[u0 + cut[k]]), 256) + 256;
         ws_off[k + 1] = ws_total;
     }
     if (!w.in.reserve(ie - ib + 16) || !w.out.reserve(oe - ob + 16) || !w.meta.reserve(m_total) || !w.ws.reserve(ws_total) ||
@@ -197,17 +211,26 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
     for (size_t i = 0; i <= n; i++) { offs[i] = in_off[u0 + i] - ib; offs[n + 1 + i] = out_off[u0 + i] - ob; }
     uint8_t *dm = w.meta.as<uint8_t>();
     if (!CZ_CUDA(cudaMemcpyAsync(dm, offs.data(), 16 * (n + 1), cudaMemcpyHostToDevice, w.streams[0]))) return CZ_E_MEM;
-    if (!CZ_CUDA(cudaStreamSynchronize(w.streams[0]))) return CZ_E_MEM;  // `offs` is a stack-lifetime pageable buffer
+    if (any_big && !CZ_CUDA(cudaMemcpyAsync(dm + m_ids, ids.data(), 4 * n, cudaMemcpyHostToDevice, w.streams[0]))) return CZ_E_MEM;
+    if (!CZ_CUDA(cudaStreamSynchronize(w.streams[0]))) return CZ_E_MEM;  // `offs`/`ids` are stack-lifetime pageable buffers
     for (size_t k = 0; k < nsub; k++) {
         cudaStream_t st = w.streams[k % CZ_INFLATE_STREAMS];
         const size_t a = cut[k], b = cut[k + 1], nk = b - a;
         const uint64_t ia = offs[a], ibk = offs[b], oa = offs[n + 1 + a], obk = offs[n + 1 + b];
         if (ibk > ia && !CZ_CUDA(cudaMemcpyAsync(w.in.as<uint8_t>() + ia, in + ib + ia, ibk - ia, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
-        int r = launch_inflate(st, ctx, nk, w.in.as<uint8_t>(), (const uint64_t *)(dm + m_inoff) + a, w.out.as<uint8_t>(),
-                               (const uint64_t *)(dm + m_outoff) + a, (uint64_t *)(dm + m_lens) + a, (int32_t *)(dm + m_stat) + a,
-                               (uint64_t *)(dm + m_cons) + a, checks ? (uint32_t *)(dm + m_chk) + 2 * a : nullptr, window_bits,
-                               segment_mode, checks ? 3 : 0, w.ws.as<uint8_t>() + ws_off[k], ws_off[k + 1] - ws_off[k], obk - oa);
-        if (r) return r;
+        const uint32_t *d_ids = any_big ? (const uint32_t *)(dm + m_ids) + ids_at[k] : nullptr;
+        uint8_t *wsk = w.ws.as<uint8_t>() + ws_off[k];
+        const uint64_t wsk_bytes = ws_off[k + 1] - ws_off[k] - 256;
+        for (int big = 0; big < 2; big++) {
+            if (big && !n_big[k]) continue;
+            if (!big && any_big && !n_small[k]) continue;
+            int r = launch_inflate(st, ctx, nk, w.in.as<uint8_t>(), (const uint64_t *)(dm + m_inoff) + a, w.out.as<uint8_t>(),
+                                   (const uint64_t *)(dm + m_outoff) + a, (uint64_t *)(dm + m_lens) + a, (int32_t *)(dm + m_stat) + a,
+                                   (uint64_t *)(dm + m_cons) + a, checks ? (uint32_t *)(dm + m_chk) + 2 * a : nullptr, window_bits,
+                                   segment_mode, checks ? 3 : 0, big ? wsk + wsk_bytes : wsk, big ? 256 : wsk_bytes, obk - oa,
+                                   d_ids ? d_ids + (big ? n_small[k] : 0) : nullptr, big ? n_big[k] : n_small[k], big);
+            if (r) return r;
+        }
         if (obk > oa && !CZ_CUDA(cudaMemcpyAsync(out + ob + oa, w.out.as<uint8_t>() + oa, obk - oa, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
         if (!CZ_CUDA(cudaMemcpyAsync(w.res_lens + a, dm + m_lens + 8 * a, 8 * nk, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
         if (!CZ_CUDA(cudaMemcpyAsync(w.res_stat + a, dm + m_stat + 4 * a, 4 * nk, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;

@@ -54,7 +54,7 @@ inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
 int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out,
                    const uint64_t *d_out_off, uint64_t *d_out_lens, int32_t *d_statuses, uint64_t *d_in_consumed,
                    uint32_t *d_checks, int window_bits, int segment_mode, int check_kind, void *d_ws, uint64_t ws_bytes,
-                   uint64_t total_out_bytes);
+                   uint64_t total_out_bytes, const uint32_t *d_ids, size_t n_ids, int big);
 uint64_t inflate_workspace_bytes(size_t n, uint64_t total_out_bytes);
 
 // batched inflate over host memory (host.cu); segment_mode / checks as in cz_inflate_segments_device

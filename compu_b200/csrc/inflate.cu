@@ -88,17 +88,17 @@ uint64_t inflate_workspace_bytes(size_t n, uint64_t total_out_bytes) {
 
 template <int WA, int WB>
 static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams &P, void *d_ws, uint64_t ws_bytes,
-                            uint64_t total_out_bytes) {
-    if (ws_bytes < inflate_workspace_bytes(P.n, total_out_bytes)) {
+                            uint64_t total_out_bytes, size_t n_span) {
+    if (ws_bytes < inflate_workspace_bytes(n_span, total_out_bytes)) {
         set_error("inflate workspace too small: %llu < %llu (see cz_inflate_workspace_bytes)", (unsigned long long)ws_bytes,
-                  (unsigned long long)inflate_workspace_bytes(P.n, total_out_bytes));
+                  (unsigned long long)inflate_workspace_bytes(n_span, total_out_bytes));
         return CZ_E_MEM;
     }
     czk::TwoPhaseParams Q;
     Q.base = P;
     Q.counter_b = (unsigned long long *)((uint8_t *)d_ws + 128);
     Q.meta = (czk::TokMeta *)((uint8_t *)d_ws + two_phase_meta_off());
-    Q.tok = (uint32_t *)((uint8_t *)d_ws + two_phase_tok_off(P.n));
+    Q.tok = (uint32_t *)((uint8_t *)d_ws + two_phase_tok_off(n_span));
     auto ka = czk::inflate_tok_kernel<WA>;
     auto kb = czk::inflate_lz_kernel<WB>;
     const size_t smem = czk::inflate_tok_smem_bytes<WA>();
@@ -116,7 +116,9 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
     if (ga > gmax) ga = gmax;
     ka<<<(unsigned)ga, WA * 32, smem, st>>>(Q);
     uint64_t gb = (P.n + WB - 1) / WB;
-    gmax = (uint64_t)ctx->sm_count * per_sm_b[d];
+    static int lz_cap = -1;  // experiment knob: CTAs of phase B per SM (fewer streams in flight => their windows fit L2)
+    if (lz_cap < 0) { const char *e = getenv("CZ_LZ_CTAS_PER_SM"); lz_cap = e ? atoi(e) : 0; }
+    gmax = (uint64_t)ctx->sm_count * (lz_cap > 0 && lz_cap < per_sm_b[d] ? lz_cap : per_sm_b[d]);
     if (gb > gmax) gb = gmax;
     kb<<<(unsigned)gb, WB * 32, 0, st>>>(Q);
     return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
@@ -139,8 +141,8 @@ static InflateCfg pick_cfg() {
 int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out,
                    const uint64_t *d_out_off, uint64_t *d_out_lens, int32_t *d_statuses, uint64_t *d_in_consumed,
                    uint32_t *d_checks, int window_bits, int segment_mode, int check_kind, void *d_ws, uint64_t ws_bytes,
-                   uint64_t total_out_bytes) {
-    if (n == 0) return 0;
+                   uint64_t total_out_bytes, const uint32_t *d_ids, size_t n_ids, int big) {
+    if (n == 0 || (d_ids && n_ids == 0)) return 0;
     if (n > 0xfffffff0u) { set_error("too many units in one launch"); return CZ_E_STREAM; }
     if (ws_bytes < 256 || !d_ws) { set_error("inflate workspace too small"); return CZ_E_MEM; }
     if (!(window_bits == -15 || window_bits == 15 || window_bits == 31 || window_bits == 47) && !segment_mode) {
@@ -150,19 +152,23 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
     czk::InflateParams P;
     P.in = d_in; P.in_off = d_in_off; P.out = d_out; P.out_off = d_out_off; P.out_lens = d_out_lens; P.statuses = d_statuses;
     P.in_consumed = d_in_consumed; P.checks = d_checks; P.counter = (unsigned long long *)d_ws; P.crc = ctx->d_crc;
-    P.n = (uint32_t)n; P.window_bits = window_bits; P.segment_mode = segment_mode; P.check_kind = check_kind;
+    P.n = (uint32_t)(d_ids ? n_ids : n); P.ids = d_ids;
+    P.window_bits = window_bits; P.segment_mode = segment_mode; P.check_kind = check_kind;
     if (!CZ_CUDA(cudaMemsetAsync(d_ws, 0, 256, st))) return CZ_E_MEM;
     InflateCfg c = pick_cfg();
+    // big units (one stream is megabytes): one WARP per stream, a single decoder lane feeding warp-cooperative LZ77 rounds —
+    // about 6x the single-stream speed of the lane-per-stream kernels, which only pay off across thousands of streams
+    if (big) return launch_cfg<1, 8>(st, ctx, P);
 #define CZ_CFG(d, w) if (c.D == d && c.W == w) return launch_cfg<d, w>(st, ctx, P)
     CZ_CFG(1, 8); CZ_CFG(2, 8); CZ_CFG(4, 7); CZ_CFG(4, 4); CZ_CFG(8, 7); CZ_CFG(8, 4); CZ_CFG(8, 2); CZ_CFG(16, 3);
     CZ_CFG(16, 1); CZ_CFG(32, 1);
 #undef CZ_CFG
-    if (c.D == -2 && c.W == 14) return launch_two_phase<14, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes);
-    if (c.D == -2 && c.W == 12) return launch_two_phase<12, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes);
-    if (c.D == -2 && c.W == 10) return launch_two_phase<10, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes);
-    if (c.D == -2 && c.W == 7) return launch_two_phase<7, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes);
-    if (c.D == -2 && c.W == 4) return launch_two_phase<14, 4>(st, ctx, P, d_ws, ws_bytes, total_out_bytes);
-    if (c.D == -2 && c.W == 16) return launch_two_phase<14, 16>(st, ctx, P, d_ws, ws_bytes, total_out_bytes);
+    if (c.D == -2 && c.W == 14) return launch_two_phase<14, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && c.W == 12) return launch_two_phase<12, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && c.W == 10) return launch_two_phase<10, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && c.W == 7) return launch_two_phase<7, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && c.W == 4) return launch_two_phase<14, 4>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && c.W == 16) return launch_two_phase<14, 16>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
     // D = -1: lane-per-stream canonical-decode kernel with W warps per CTA
     if (c.D == -1 && c.W == 14) return launch_lc<14>(st, ctx, P);
     if (c.D == -1 && c.W == 12) return launch_lc<12>(st, ctx, P);
@@ -202,7 +208,7 @@ extern "C" int cz_inflate_batch_device(void *cuda_stream, size_t n, const uint8_
     DeviceCtx *ctx = device_ctx(dev);
     if (!ctx) return CZ_E_NO_DEVICE;
     return launch_inflate((cudaStream_t)cuda_stream, ctx, n, d_in, d_in_offsets, d_out, d_out_offsets, d_out_lens, d_statuses,
-                          d_in_consumed, nullptr, window_bits, 0, 0, d_workspace, workspace_bytes, total_out_bytes);
+                          d_in_consumed, nullptr, window_bits, 0, 0, d_workspace, workspace_bytes, total_out_bytes, nullptr, 0, 0);
 }
 
 extern "C" int cz_inflate_segments_device(void *cuda_stream, size_t n, const uint8_t *d_in, const uint64_t *d_in_offsets,
@@ -213,5 +219,5 @@ extern "C" int cz_inflate_segments_device(void *cuda_stream, size_t n, const uin
     DeviceCtx *ctx = device_ctx(dev);
     if (!ctx) return CZ_E_NO_DEVICE;
     return launch_inflate((cudaStream_t)cuda_stream, ctx, n, d_in, d_in_offsets, d_out, d_out_offsets, d_out_lens, d_statuses,
-                          nullptr, d_checks, -15, 1, d_checks ? 3 : 0, d_workspace, workspace_bytes, total_out_bytes);
+                          nullptr, d_checks, -15, 1, d_checks ? 3 : 0, d_workspace, workspace_bytes, total_out_bytes, nullptr, 0, 0);
 }

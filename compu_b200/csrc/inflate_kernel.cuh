@@ -43,6 +43,7 @@ struct InflateParams {
     uint32_t *checks;         // 2n {adler32, crc32} or null
     unsigned long long *counter;  // work counter, zero before launch
     const CrcTables *crc;     // needed when a CRC is computed
+    const uint32_t *ids;      // optional: the n units to process are ids[0..n) (indices into the offset arrays); null = 0..n-1
     uint32_t n;
     int32_t window_bits;      // -15 raw, 15 zlib, 31 gzip, 47 auto
     int32_t segment_mode;     // 1: raw full-flush segments: end of input at a block boundary is success
@@ -462,7 +463,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
             unsigned long long u = atomicAdd(P.counter, 1ull);
             if (u >= P.n) st = SS_EXIT;
             else {
-                unit = (uint32_t)u;
+                unit = P.ids ? P.ids[u] : (uint32_t)u;
                 uint64_t i0 = P.in_off[unit], i1 = P.in_off[unit + 1], o0 = P.out_off[unit], o1 = P.out_off[unit + 1];
                 in_base = P.in + i0; in_len = i1 - i0;
                 out_base = P.out + o0; out_cap = o1 - o0; out_pos = 0; ck_pos = 0;

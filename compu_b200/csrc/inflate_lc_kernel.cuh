@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lc_kernel(InflateParams P)
             unsigned long long u = atomicAdd(P.counter, 1ull);
             if (u >= P.n) st = SS_EXIT;
             else {
-                unit = (uint32_t)u;
+                unit = P.ids ? P.ids[u] : (uint32_t)u;
                 uint64_t i0 = P.in_off[unit], i1 = P.in_off[unit + 1], o0 = P.out_off[unit], o1 = P.out_off[unit + 1];
                 in_base = P.in + i0; in_len = i1 - i0;
                 out = P.out + o0; cap = o1 - o0; pos = 0;

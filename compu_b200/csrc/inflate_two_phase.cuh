@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
             unsigned long long u = atomicAdd(P.counter, 1ull);
             if (u >= P.n) st = SS_EXIT;
             else {
-                unit = (uint32_t)u;
+                unit = P.ids ? P.ids[u] : (uint32_t)u;
                 uint64_t i0 = P.in_off[unit], i1 = P.in_off[unit + 1], o0 = P.out_off[unit], o1 = P.out_off[unit + 1];
                 in_base = P.in + i0; in_len = i1 - i0;
                 cap = o1 - o0; pos = 0;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lz_kernel(TwoPhaseParams Q
         if (lane == 0) u64 = atomicAdd(Q.counter_b, 1ull);
         u64 = __shfl_sync(CZK_FULL, u64, 0);
         if (u64 >= P.n) break;
-        const uint32_t unit = (uint32_t)u64;
+        const uint32_t unit = P.ids ? P.ids[u64] : (uint32_t)u64;
         const TokMeta m = Q.meta[unit];
         const uint64_t o0 = P.out_off[unit];
         uint8_t *ob = P.out + o0;
@@ -363,7 +363,13 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lz_kernel(TwoPhaseParams Q
                         if (tk >> 31) val = (tk >> (8 * off)) & 0xff;
                         else {
                             uint32_t dist = (tk >> 9) & 0xffffu;
-                            if (off >= dist) off %= dist;
+                            if (off >= dist) {  // overlapping copy: off mod dist without the integer-division sequence (off < 512)
+                                uint32_t q = (uint32_t)__float2uint_rz(__fdividef((float)off, (float)dist));
+                                uint32_t r = off - q * dist;
+                                if ((int)r < 0) r += dist;
+                                if (r >= dist) r -= dist;
+                                off = r;
+                            }
                             int src = (int)tpp - (int)dist + (int)off;  // batch-relative source index (< tpp)
                             int lo2 = rel > 0 ? rel : 0;
                             if (src >= lo2) { need = true; srcl = src - rel; }

@@ -289,6 +289,8 @@ inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
     }
     return r;
 }
+inline float __fdividef(float a, float b) { return a / b; }
+inline unsigned __float2uint_rz(float x) { return (unsigned)x; }
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
 inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) {
     return (unsigned long long)(((unsigned __int128)a * b) >> 64);

@@ -127,3 +127,21 @@ def test_inflate_config_sweep_is_consistent(alice):
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
                            cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
         assert r.returncode == 0 and "ok" in r.stdout, (cfg, r.stdout, r.stderr)
+
+
+def test_mixed_big_and_small_units_vs_oracle(alice):
+    # ragged batch (cfg5 in miniature): megabyte streams go to the warp-per-stream kernel, small ones to the two-phase path
+    rng = np.random.default_rng(11)
+    big = alice * 20
+    datas = []
+    for i in range(60):
+        n = int(rng.choice([4096, 20000, 65536, 300000, 1 << 21, 3_000_000])) if i % 7 else int(rng.integers(0, 2000))
+        o = int(rng.integers(0, len(big) - n))
+        datas.append(big[o:o + n])
+    for wbits in (15, 31):
+        streams = [zcomp(d, 6, wbits) for d in datas]
+        caps = [len(d) for d in datas]
+        outs, st, lens, cons = batch.inflate_batch(streams, caps, wbits)
+        ref_outs, ref_st, _ = oracle_inflate(streams, caps, wbits)
+        assert_inflate_parity(outs, st, ref_outs, ref_st, "mixed wbits %d" % wbits)
+        assert list(cons) == [len(s) for s in streams]

@@ -3,7 +3,9 @@
 
 ncu's CSV source page is per SASS instruction; this joins it with `nvdisasm -g` line info of the matching cubin so the
 hot source lines (instructions executed, stall samples) can be read without the GUI.
-usage: ncu_lines.py report.ncu-rep lib.so kernel_substring [top_n]
+usage: ncu_lines.py report.ncu-rep lib.so kernel_substring [top_n] [mangled_substring]
+(kernel_substring selects the kernel section of the report; mangled_substring, default = kernel_substring, selects the
+function in the cubin, e.g. inflate_tok_kernelILi14E for one template instantiation)
 """
 import csv
 import os
@@ -13,9 +15,14 @@ import sys
 import tempfile
 
 
+def r_join(r):
+    return ",".join(r)
+
+
 def main():
     rep, so, kname = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    mangled = sys.argv[5] if len(sys.argv) > 5 else kname
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
     sass_lines = None
@@ -23,7 +30,7 @@ def main():
         if not f.endswith(".cubin"):
             continue
         out = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout
-        if kname in out:
+        if mangled in out:
             sass_lines = out.splitlines()
             break
     assert sass_lines, "kernel not found in any cubin"
@@ -33,7 +40,7 @@ def main():
     inst_lines = []
     for ln in sass_lines:
         if ln.startswith(".text.") or re.match(r"\s*\.section\s+\.text\.", ln):
-            infn = kname in ln
+            infn = mangled in ln
             continue
         if not infn:
             continue
@@ -45,10 +52,15 @@ def main():
             inst_lines.append(cur)
     csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(csvtxt.splitlines()))
+    # the report may hold several kernels: take the section whose "Kernel Name" row matches
+    starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
+    sec = next((i for i in starts if kname in r_join(rows[i])), starts[0] if starts else 0)
+    nxt = next((i for i in starts if i > sec), len(rows))
+    rows = rows[sec:nxt]
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hdr_i]
     ci = {n: hdr.index(n) for n in ("Instructions Executed", "# Samples", "Source", "Thread Instructions Executed")}
-    data = rows[hdr_i + 1:]
+    data = [r for r in rows[hdr_i + 1:] if len(r) > max(ci.values())]
     if len(data) != len(inst_lines):
         print("warning: %d SASS rows in report vs %d in cubin" % (len(data), len(inst_lines)))
     agg = {}
