@@ -146,7 +146,7 @@ struct EngineJob {
 static uint64_t batch_bytes_limit() {
     static uint64_t v = 0;
     if (!v) {
-        v = 256ull << 20;
+        v = 1024ull << 20;  // large enough that the warp-per-segment passes (checksum, chains, parse) fill the machine
         if (const char *e = getenv("CZ_BATCH_MB")) { long m = atol(e); if (m >= 1 && m <= 8192) v = (uint64_t)m << 20; }
     }
     return v;

@@ -242,3 +242,77 @@ def test_device_api_segments(alice):
     assert d_st2.tolist() == [2] * n
     assert d_back[:total].cpu().numpy().tobytes() == b"".join(segs)
     assert (d_chk2.cpu().numpy().view(np.uint32) == chk).all()
+
+
+def _synth_host(kind, nbytes, seed=4242):
+    L = _lib.lib()
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    import conftest
+    corpus = np.frombuffer(conftest.read_golden("alice29.txt"), dtype=np.uint8)
+    model = np.zeros(int(L.cz_synth_model_bytes()), dtype=np.uint8)
+    assert L.cz_synth_build_model(p(corpus), len(corpus), p(model)) == 0
+    n = nbytes // 65536
+    offs = np.arange(n + 1, dtype=np.uint64) * 65536
+    buf = np.empty(n * 65536 + 16, dtype=np.uint8)
+    assert L.cz_synth_fill_host(kind, seed, n, p(buf), p(offs), p(model)) == 0
+    return buf, n * 65536
+
+
+def test_full_size_gzip_1gib_roundtrip_with_parallel_crc_combine():
+    """BASELINE.json configs[3] at full size: gzip encode + decode of 1 GiB mixed-entropy data; the CRC-32 in the trailer comes
+    from the per-segment parallel combine and must equal zlib.crc32 of the whole input (checksum of checksums)."""
+    L = _lib.lib()
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    src, n = _synth_host(3, 1 << 30)
+    cap = int(L.cz_deflate_bound(n, 31, 1 << 20))
+    out = np.empty(cap + 16, dtype=np.uint8)
+    out_len = ctypes.c_uint64(0)
+    nseg = ctypes.c_uint64(0)
+    idx = np.zeros(n // (1 << 20) + 8, dtype=np.uint64)
+    rc = L.cz_deflate_segmented(p(src), n, p(out), cap, ctypes.byref(out_len), 6, 31, 0, 1 << 20, 0, p(idx), len(idx), ctypes.byref(nseg))
+    _lib.check(rc, "cz_deflate_segmented")
+    clen = out_len.value
+    assert int.from_bytes(out[clen - 8:clen - 4].tobytes(), "little") == zlib.crc32(src[:n])
+    assert int.from_bytes(out[clen - 4:clen].tobytes(), "little") == n & 0xffffffff
+    # decode: segment-parallel with the side index (checks the combined CRC against the trailer on the way)
+    back = np.empty(n + 16, dtype=np.uint8)
+    got = ctypes.c_uint64(0)
+    rc = L.cz_inflate_segmented(p(out), clen, p(back), n, ctypes.byref(got), 31, 1 << 20, p(idx), nseg.value, 0)
+    _lib.check(rc, "cz_inflate_segmented")
+    assert got.value == n and np.array_equal(back[:n], src[:n])
+    # and the reference decoder's L0 accepts it as ONE gzip member (sampled: the first 64 MiB of output)
+    d = zlib.decompressobj(31)
+    head = d.decompress(out[:clen].tobytes(), 64 << 20)
+    assert head == src[:64 << 20].tobytes()
+
+
+def test_full_size_deflate_4gib_single_stream():
+    """BASELINE.json configs[2] at full size: one 4 GiB buffer -> ONE valid zlib stream of full-flush segments. Properties:
+    Adler-32 in the trailer equals zlib.adler32 of the whole input; segment-parallel inflate round-trips bit-exactly; >4 GiB-safe
+    offsets (the compressed stream and the index are addressed with 64-bit offsets)."""
+    L = _lib.lib()
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    src, n = _synth_host(0, 1 << 32)
+    assert n == 1 << 32
+    cap = int(L.cz_deflate_bound(n, 15, 1 << 20))
+    out = np.empty(cap + 16, dtype=np.uint8)
+    out_len = ctypes.c_uint64(0)
+    nseg = ctypes.c_uint64(0)
+    idx = np.zeros(n // (1 << 20) + 8, dtype=np.uint64)
+    rc = L.cz_deflate_segmented(p(src), n, p(out), cap, ctypes.byref(out_len), 6, 15, 0, 1 << 20, 0, p(idx), len(idx), ctypes.byref(nseg))
+    _lib.check(rc, "cz_deflate_segmented")
+    clen = out_len.value
+    assert nseg.value == 4096
+    adler = 1
+    for o in range(0, n, 1 << 30):
+        adler = zlib.adler32(src[o:o + (1 << 30)], adler)
+    assert int.from_bytes(out[clen - 4:clen].tobytes(), "big") == adler
+    ratio = n / clen
+    assert ratio > 2.0, ratio
+    back = np.empty(n + 16, dtype=np.uint8)
+    got = ctypes.c_uint64(0)
+    rc = L.cz_inflate_segmented(p(out), clen, p(back), n, ctypes.byref(got), 15, 1 << 20, p(idx), nseg.value, 0)
+    _lib.check(rc, "cz_inflate_segmented")
+    assert got.value == n
+    for o in range(0, n, 1 << 28):
+        assert np.array_equal(back[o:o + (1 << 28)], src[o:o + (1 << 28)])
