@@ -265,14 +265,15 @@ __host__ __device__ inline void huff_build_lengths(const uint32_t *freq_in, uint
     }
     uint32_t root = next - 1;
     s.depth[root] = 0;
-    for (uint32_t i = root; i-- > 0;) s.depth[i] = (uint8_t)(s.depth[s.parent[i]] + 1);
     for (uint32_t b = 0; b <= 15; b++) s.bl_count[b] = 0;
+    // depths top-down with clamping, exactly like zlib's gen_bitlen: EVERY node (internal ones too) that would sit below
+    // maxbits is clamped and counted, so that overflow / 2 is the number of repair steps that restores the Kraft sum
     int overflow = 0;
-    for (uint32_t i = 0; i < nleaf; i++) {
-        uint32_t d = s.depth[i];
+    for (uint32_t i = root; i-- > 0;) {
+        uint32_t d = (uint32_t)s.depth[s.parent[i]] + 1;
         if (d > maxbits) { d = maxbits; overflow++; }
         s.depth[i] = (uint8_t)d;
-        s.bl_count[d]++;
+        if (i < nleaf) s.bl_count[d]++;
     }
     if (overflow > 0) {
         // zlib gen_bitlen: repair the Kraft sum by moving leaves

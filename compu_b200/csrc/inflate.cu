@@ -86,7 +86,7 @@ uint64_t inflate_workspace_bytes(size_t n, uint64_t total_out_bytes) {
     return two_phase_tok_off(n) + 4 * (total_out_bytes + 8 * (uint64_t)n) + 256;
 }
 
-template <int WA, int WB>
+template <int WA, int WB, int H>
 static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams &P, void *d_ws, uint64_t ws_bytes,
                             uint64_t total_out_bytes, size_t n_span) {
     if (ws_bytes < inflate_workspace_bytes(n_span, total_out_bytes)) {
@@ -100,7 +100,7 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
     Q.meta = (czk::TokMeta *)((uint8_t *)d_ws + two_phase_meta_off());
     Q.tok = (uint32_t *)((uint8_t *)d_ws + two_phase_tok_off(n_span));
     auto ka = czk::inflate_tok_kernel<WA>;
-    auto kb = czk::inflate_lz_kernel<WB>;
+    auto kb = czk::inflate_lz_kernel<WB, H>;
     const size_t smem = czk::inflate_tok_smem_bytes<WA>();
     static bool configured[64] = {};
     static int per_sm_a[64], per_sm_b[64];
@@ -163,12 +163,11 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
     CZ_CFG(1, 8); CZ_CFG(2, 8); CZ_CFG(4, 7); CZ_CFG(4, 4); CZ_CFG(8, 7); CZ_CFG(8, 4); CZ_CFG(8, 2); CZ_CFG(16, 3);
     CZ_CFG(16, 1); CZ_CFG(32, 1);
 #undef CZ_CFG
-    if (c.D == -2 && c.W == 14) return launch_two_phase<14, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
-    if (c.D == -2 && c.W == 12) return launch_two_phase<12, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
-    if (c.D == -2 && c.W == 10) return launch_two_phase<10, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
-    if (c.D == -2 && c.W == 7) return launch_two_phase<7, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
-    if (c.D == -2 && c.W == 4) return launch_two_phase<14, 4>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
-    if (c.D == -2 && c.W == 16) return launch_two_phase<14, 16>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    // D = -2: two-phase, W = rounds per iteration of phase B (loads in flight per lane)
+    if (c.D == -2 && (c.W == 14 || c.W == 4)) return launch_two_phase<14, 8, 4>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && c.W == 1) return launch_two_phase<14, 8, 1>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && c.W == 2) return launch_two_phase<14, 8, 2>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && c.W == 8) return launch_two_phase<14, 8, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
     // D = -1: lane-per-stream canonical-decode kernel with W warps per CTA
     if (c.D == -1 && c.W == 14) return launch_lc<14>(st, ctx, P);
     if (c.D == -1 && c.W == 12) return launch_lc<12>(st, ctx, P);

@@ -297,7 +297,7 @@ constexpr size_t inflate_tok_smem_bytes() { return 128 + WARPS * 256 + sizeof(Lc
 
 // ---------------------------------------------------------------------------------------------------------------
 // Phase B: one warp per unit.
-template <int WARPS>
+template <int WARPS, int H>
 __global__ void __launch_bounds__(WARPS * 32) inflate_lz_kernel(TwoPhaseParams Q) {
     const InflateParams &P = Q.base;
     __shared__ uint32_t crc_tab[256 + 34];
@@ -341,49 +341,70 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lz_kernel(TwoPhaseParams Q
                 const uint32_t total = __shfl_sync(CZK_FULL, pos, 31);
                 pos -= tl;
                 const uint64_t a0 = (uint64_t)(uintptr_t)ob + opos;   // absolute address of batch byte 0
-                int rel = -(int)(a0 & 31);                             // batch-relative index of this round's lane 0
+                int rel = -(int)(a0 & 31);                             // batch-relative index of this iteration's first byte
                 uint32_t cnt_before = 0;
                 uint8_t *obp = ob + opos;
-                for (; rel < (int)total; rel += 32) {
-                    // which tokens start inside this round? (every token covers at least one byte)
-                    uint32_t bit = (lane < nt && (int)pos >= rel && (int)pos < rel + 32) ? 1u << ((int)pos - rel) : 0u;
-                    uint32_t S = __reduce_or_sync(CZK_FULL, bit);
-                    int j = rel + (int)lane;
-                    bool active = j >= 0 && j < (int)total;
-                    // lane holding the token that covers byte j
-                    int src_lane = (int)cnt_before + __popc(S & (0xffffffffu >> (31 - lane))) - 1;
-                    cnt_before += __popc(S);
-                    uint32_t val = 0;
-                    bool need = false;
-                    int srcl = 0;
-                    uint32_t tk = __shfl_sync(CZK_FULL, t, src_lane & 31);
-                    uint32_t tpp = __shfl_sync(CZK_FULL, pos, src_lane & 31);
-                    if (active) {
-                        uint32_t off = (uint32_t)j - tpp;
-                        if (tk >> 31) val = (tk >> (8 * off)) & 0xff;
-                        else {
-                            uint32_t dist = (tk >> 9) & 0xffffu;
-                            if (off >= dist) {  // overlapping copy: off mod dist without the integer-division sequence (off < 512)
-                                uint32_t q = (uint32_t)__float2uint_rz(__fdividef((float)off, (float)dist));
-                                uint32_t r = off - q * dist;
-                                if ((int)r < 0) r += dist;
-                                if (r >= dist) r -= dist;
-                                off = r;
+                // H sector-aligned 32-byte rounds per iteration. All back-reference loads of the iteration are issued before
+                // the first one is consumed (H loads in flight per lane: the kernel is bound by the latency of these
+                // loads, the windows of the streams in flight exceed L2); sources produced inside the iteration come from
+                // registers by shuffle.
+                for (; rel < (int)total; rel += 32 * H) {
+                    uint32_t val[H];
+                    int srcl[H], srch[H];  // source lane / source round inside this iteration (srch < 0: value is final)
+                    const int lo2 = rel > 0 ? rel : 0;
+#pragma unroll
+                    for (int h = 0; h < H; h++) {
+                        const int r0 = rel + 32 * h;
+                        // which tokens start inside this round? (every token covers at least one byte)
+                        uint32_t bit = (lane < nt && (int)pos >= r0 && (int)pos < r0 + 32) ? 1u << ((int)pos - r0) : 0u;
+                        uint32_t S = __reduce_or_sync(CZK_FULL, bit);
+                        const int j = r0 + (int)lane;
+                        const bool active = j >= 0 && j < (int)total;
+                        // lane holding the token that covers byte j
+                        int src_lane = (int)cnt_before + __popc(S & (0xffffffffu >> (31 - lane))) - 1;
+                        cnt_before += __popc(S);
+                        uint32_t tk = __shfl_sync(CZK_FULL, t, src_lane & 31);
+                        uint32_t tpp = __shfl_sync(CZK_FULL, pos, src_lane & 31);
+                        val[h] = 0; srcl[h] = 0; srch[h] = -1;
+                        if (active) {
+                            uint32_t off = (uint32_t)j - tpp;
+                            if (tk >> 31) val[h] = (tk >> (8 * off)) & 0xff;
+                            else {
+                                uint32_t dist = (tk >> 9) & 0xffffu;
+                                if (off >= dist) {  // overlapping copy: off mod dist without the integer-division sequence (off < 512)
+                                    uint32_t q = (uint32_t)__float2uint_rz(__fdividef((float)off, (float)dist));
+                                    uint32_t r = off - q * dist;
+                                    if ((int)r < 0) r += dist;
+                                    if (r >= dist) r -= dist;
+                                    off = r;
+                                }
+                                int src = (int)tpp - (int)dist + (int)off;  // batch-relative source index (< tpp)
+                                if (src >= lo2) { srch[h] = (src - rel) >> 5; srcl[h] = (src - rel) & 31; }
+                                else val[h] = obp[src];                     // bytes of earlier iterations / batches
                             }
-                            int src = (int)tpp - (int)dist + (int)off;  // batch-relative source index (< tpp)
-                            int lo2 = rel > 0 ? rel : 0;
-                            if (src >= lo2) { need = true; srcl = src - rel; }
-                            else val = obp[src];                        // bytes of earlier rounds / batches
                         }
                     }
-                    uint32_t pend = __ballot_sync(CZK_FULL, need);
-                    while (pend) {
-                        uint32_t v = __shfl_sync(CZK_FULL, val, srcl);
-                        bool src_ready = !((pend >> srcl) & 1u);
-                        if (need && src_ready) { val = v; need = false; }
-                        pend = __ballot_sync(CZK_FULL, need);
+#pragma unroll
+                    for (int h = 0; h < H; h++) {
+#pragma unroll
+                        for (int hp = 0; hp < h; hp++) {  // sources in earlier rounds of this iteration: already final
+                            uint32_t v = __shfl_sync(CZK_FULL, val[hp], srcl[h]);
+                            if (srch[h] == hp) { val[h] = v; srch[h] = -1; }
+                        }
+                        bool need = srch[h] == h;
+                        uint32_t pend = __ballot_sync(CZK_FULL, need);
+                        while (pend) {
+                            uint32_t v = __shfl_sync(CZK_FULL, val[h], srcl[h]);
+                            bool src_ready = !((pend >> srcl[h]) & 1u);
+                            if (need && src_ready) { val[h] = v; need = false; }
+                            pend = __ballot_sync(CZK_FULL, need);
+                        }
                     }
-                    if (active) obp[j] = (uint8_t)val;
+#pragma unroll
+                    for (int h = 0; h < H; h++) {
+                        const int j = rel + 32 * h + (int)lane;
+                        if (j >= 0 && j < (int)total) obp[j] = (uint8_t)val[h];
+                    }
                     __syncwarp();
                 }
                 opos += total;

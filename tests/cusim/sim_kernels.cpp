@@ -40,7 +40,8 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
             TwoPhaseParams Q;
             Q.base = P; Q.tok = tok.data(); Q.meta = meta.data(); Q.counter_b = &counter_b;
             cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2>, Q);
-            cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2>, Q);
+            if (seed & 1) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 4>, Q);
+            else cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 2>, Q);
             for (size_t i = total_out + 8 * n; i < tok.size(); i++) if (tok[i] != 0xDEADBEEFu) return -2;  // token area overrun
             break;
         }

@@ -109,3 +109,9 @@ extern "C" long model_deflate_segment(const uint8_t *seg, uint32_t n, uint8_t *o
     if (bw.overflow) return -1;
     return (long)(bw.nbits >> 3);
 }
+
+// length-limited Huffman code lengths of the shared core (for property tests)
+extern "C" void model_huff_lengths(const uint32_t *freq, uint32_t n, uint32_t maxbits, uint8_t *lens) {
+    static HuffScratch hs;
+    huff_build_lengths(freq, n, maxbits, lens, hs, 1);
+}

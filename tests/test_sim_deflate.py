@@ -111,3 +111,52 @@ def test_sim_segment_join_is_one_valid_stream(alice):
         assert zlib.decompressobj(-15).decompress(piece) == alice[i * 16384:min((i + 1) * 16384, 100000)]
         o += int(sz)
     assert s[o:o + 2] == b"\x03\x00"
+
+
+def test_length_limited_huffman_is_complete_and_within_limit():
+    """Kraft sum of the code lengths must be exactly 1 (zlib rejects anything else: "invalid code lengths set" /
+    "invalid literal/lengths set") and no length may exceed the limit — including skewed distributions that force the
+    overflow repair (Fibonacci-like frequencies make the unrestricted tree as deep as the alphabet)."""
+    L = model_lib()
+    rng = np.random.default_rng(5)
+    cases = []
+    for n, maxbits in ((19, 7), (30, 15), (286, 15)):
+        fib = [1, 1]
+        while len(fib) < n:
+            fib.append(min(fib[-1] + fib[-2], 1 << 22))
+        cases.append((n, maxbits, np.array(fib[:n], dtype=np.uint32)))
+        cases.append((n, maxbits, np.array(fib[:n][::-1], dtype=np.uint32)))
+        for _ in range(300):
+            k = int(rng.integers(1, n + 1))
+            f = np.zeros(n, dtype=np.uint32)
+            idx = rng.choice(n, k, replace=False)
+            shape = rng.choice(["flat", "geo", "zipf", "rand"])
+            if shape == "flat":
+                f[idx] = rng.integers(1, 4, k)
+            elif shape == "geo":
+                f[idx] = np.minimum(1.7 ** np.minimum(np.arange(k), 40), float(1 << 22)).astype(np.uint32)
+            elif shape == "zipf":
+                f[idx] = np.maximum(1, (100000 / (1 + np.arange(k)) ** 2).astype(np.uint32))
+            else:
+                f[idx] = rng.integers(1, 1 << 16, k)
+            cases.append((n, maxbits, f))
+    for n, maxbits, f in cases:
+        lens = np.zeros(n, dtype=np.uint8)
+        L.model_huff_lengths(f.ctypes.data_as(ctypes.c_void_p), n, maxbits, lens.ctypes.data_as(ctypes.c_void_p))
+        used = lens[lens > 0]
+        assert used.max() <= maxbits
+        assert (lens[f > 0] > 0).all()
+        kraft = sum(1 << (maxbits - int(l)) for l in used)
+        assert kraft == 1 << maxbits, (n, maxbits, kraft, f.tolist())
+
+
+def test_sim_deflate_near_random_1mib_segment():
+    # regression: near-random data drives the code-length code past 7 bits (the repair path of the length-limited Huffman)
+    rng = np.random.default_rng(698)
+    parts = []
+    for i in range(64):
+        parts.append(rng.integers(0, 256, 4096, dtype=np.uint8).tobytes() if i % 10 else bytes(rng.integers(97, 123, 4096, dtype=np.uint8)))
+    data = b"".join(parts) * 2
+    streams, st, _, _, _ = simlib.sim_deflate([data], seg_bytes=1 << 20, window_bits=-15, piece_mode=1)
+    assert st[0] == 2
+    assert zlib.decompressobj(-15).decompress(streams[0]) == data
