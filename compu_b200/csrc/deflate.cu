@@ -95,12 +95,23 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
     if (L.d_unit_out_pos_ret) *L.d_unit_out_pos_ret = P.unit_out_pos;
     if (L.d_total_ret) *L.d_total_ret = P.total_out;
     const unsigned nseg = P.nseg, nun = P.n_units, nsl = P.n_slots;
-    if (P.check_kind) czk::deflate_checksum_kernel<<<(nseg + 3) / 4, 128, 0, st>>>(P);
+    if (P.check_kind) czk::deflate_checksum_kernel<<<nseg < 65535u * 8u ? nseg : 65535u * 8u, 128, 0, st>>>(P);
     if (!P.tune.level0 && !P.tune.huffman_only && !P.tune.rle_only) {
         unsigned grid = nseg < (unsigned)ctx->sm_count * 12u ? nseg : (unsigned)ctx->sm_count * 12u;
         czk::deflate_chain_kernel<<<grid, 32, 0, st>>>(P);
     }
-    czk::deflate_match_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
+    if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || getenv("CZ_MATCH_SIMPLE")) {
+        czk::deflate_match_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
+    } else {
+        static bool configured[64] = {};
+        const size_t smem = czk::deflate_match_tiled_smem();
+        if (!configured[ctx->dev & 63]) {
+            if (!CZ_CUDA(cudaFuncSetAttribute(czk::deflate_match_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return CZ_E_MEM;
+            configured[ctx->dev & 63] = true;
+        }
+        const unsigned tiles = (unsigned)((L.in_bytes >> 12) + L.nseg + 1);
+        czk::deflate_match_tiled_kernel<<<tiles, CZK_MT_THREADS, smem, st>>>(P);
+    }
     {
         unsigned grid = nseg < (unsigned)ctx->sm_count * 16u ? nseg : (unsigned)ctx->sm_count * 16u;
         czk::deflate_parse_kernel<<<grid, 32, 0, st>>>(P);

@@ -90,35 +90,57 @@ __device__ inline bool slot_to_block(const DeflateParams &P, uint32_t slot, uint
     return b < P.st[lo].nblk;
 }
 
+__device__ __forceinline__ uint32_t lds32u(const uint8_t *sb, uint32_t off) {  // unaligned little-endian word from shared memory
+    const uint32_t *w = (const uint32_t *)sb + (off >> 2);
+    return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
+}
+
 // ------------------------------------------------------------------ K0
+// One CTA (4 warps) per segment: every warp checksums a quarter, lane 0 folds the four partial values with the combine
+// identities (the same ones that fold segments into units in K5c).
 __global__ void __launch_bounds__(128) deflate_checksum_kernel(DeflateParams P) {
     __shared__ uint32_t crc_tab[256 + 34];
+    __shared__ uint32_t part_a[4], part_c[4], part_n[4];
     for (uint32_t i = threadIdx.x; i < 256 + 34; i += 128) crc_tab[i] = i < 256 ? P.crc->table[i] : P.crc->pow128[i - 256];
     __syncthreads();
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t seg = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (seg >= P.nseg) return;
-    const uint8_t *p = P.in + P.seg_off[seg];
-    const uint32_t n = seg_len(P, seg);
-    uint32_t a = 1, c = 0;
-    if (P.check_kind & 1) {
-        for (uint32_t o = 0; o < n; o += 8192) a = warp_adler32(a, p + o, n - o < 8192 ? n - o : 8192, lane);
-    }
-    if (P.check_kind & 2) {
-        uint32_t o = 0;
-        while (n - o >= 128) {
-            uint32_t q = (n - o) >> 7;
-            if (q > 32) q = 32;
-            c = warp_crc32_pieces(c, p + o, q, crc_tab, crc_tab + 256, lane);
-            o += q * 128;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t seg = blockIdx.x; seg < P.nseg; seg += gridDim.x) {
+        const uint32_t n_all = seg_len(P, seg);
+        const uint32_t q = ((n_all + 3) / 4 + 127) & ~127u;  // quarter, a multiple of the 128-byte CRC piece
+        const uint32_t b0 = warp * q < n_all ? warp * q : n_all;
+        const uint32_t n = n_all - b0 < q ? n_all - b0 : q;
+        const uint8_t *p = P.in + P.seg_off[seg] + b0;
+        uint32_t a = 1, c = 0;
+        if (P.check_kind & 1) {
+            for (uint32_t o = 0; o < n; o += 8192) a = warp_adler32(a, p + o, n - o < 8192 ? n - o : 8192, lane);
         }
-        if (o < n) {
-            uint32_t c2 = 0;
-            if (lane == 0) c2 = crc32_serial(c, p + o, n - o, crc_tab);
-            c = __shfl_sync(CZK_FULL, c2, 0);
+        if (P.check_kind & 2) {
+            uint32_t o = 0;
+            while (n - o >= 128) {
+                uint32_t k = (n - o) >> 7;
+                if (k > 32) k = 32;
+                c = warp_crc32_pieces(c, p + o, k, crc_tab, crc_tab + 256, lane);
+                o += k * 128;
+            }
+            if (o < n) {
+                uint32_t c2 = 0;
+                if (lane == 0) c2 = crc32_serial(c, p + o, n - o, crc_tab);
+                c = __shfl_sync(CZK_FULL, c2, 0);
+            }
         }
+        if (lane == 0) { part_a[warp] = a; part_c[warp] = c; part_n[warp] = n; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t A = part_a[0], C = part_c[0];
+            for (int w = 1; w < 4; w++) {
+                if (P.check_kind & 1) A = adler32_combine_u(A, part_a[w], part_n[w]);
+                if (P.check_kind & 2) C = crc32_combine_u(C, part_c[w], part_n[w]);
+            }
+            P.st[seg].adler = A;
+            P.st[seg].crc = C;
+        }
+        __syncthreads();
     }
-    if (lane == 0) { P.st[seg].adler = a; P.st[seg].crc = c; }
 }
 
 // ------------------------------------------------------------------ K1
@@ -127,8 +149,10 @@ __global__ void __launch_bounds__(128) deflate_checksum_kernel(DeflateParams P) 
 // that the 16-bit difference IS the distance) the table is swept every 16384 positions: entries 32768 or more behind are
 // re-stamped to exactly 32768 behind, which can never look recent before the next sweep. No global re-check is needed.
 #define CZK_CHAIN_SWEEP 16384u
+#define CZK_CHAIN_CHUNK 1024u
 __global__ void __launch_bounds__(32) deflate_chain_kernel(DeflateParams P) {
     __shared__ uint16_t head[1u << CZK_HASH_BITS];
+    __shared__ __align__(16) uint8_t chunk[CZK_CHAIN_CHUNK + 8];
     const uint32_t lane = threadIdx.x;
     for (uint32_t seg = blockIdx.x; seg < P.nseg; seg += gridDim.x) {
         const uint8_t *s = P.in + P.seg_off[seg];
@@ -137,33 +161,40 @@ __global__ void __launch_bounds__(32) deflate_chain_kernel(DeflateParams P) {
         __syncwarp();
         for (uint32_t i = lane; i < (1u << CZK_HASH_BITS); i += 32) head[i] = 32768;  // "32768 behind position 0"
         __syncwarp();
-        uint32_t v_next = lane + 4 <= n ? load32u(s + lane) : 0u;  // the next step's bytes are always in flight
-        for (uint32_t base = 0; base < n; base += 32) {
-            if (base && (base % CZK_CHAIN_SWEEP) == 0) {
-                for (uint32_t i = lane; i < (1u << CZK_HASH_BITS); i += 32)
-                    if (((base - (uint32_t)head[i]) & 0xffffu) >= CZK_WINDOW) head[i] = (uint16_t)((base - CZK_WINDOW) & 0xffffu);
+        for (uint32_t cb = 0; cb < n; cb += CZK_CHAIN_CHUNK) {
+            // stage the next 1 KiB (+3 bytes of lookahead) in shared memory: one memory round trip per 32 steps
+            const uint32_t cn = n - cb < CZK_CHAIN_CHUNK + 3 ? n - cb : CZK_CHAIN_CHUNK + 3;
+            __syncwarp();
+            for (uint32_t i = lane; i < cn; i += 32) chunk[i] = s[cb + i];
+            for (uint32_t i = cn + lane; i < CZK_CHAIN_CHUNK + 8; i += 32) chunk[i] = 0;
+            __syncwarp();
+            const uint32_t cend = cb + CZK_CHAIN_CHUNK < n ? cb + CZK_CHAIN_CHUNK : n;
+            for (uint32_t base = cb; base < cend; base += 32) {
+                if (base && (base % CZK_CHAIN_SWEEP) == 0) {
+                    for (uint32_t i = lane; i < (1u << CZK_HASH_BITS); i += 32)
+                        if (((base - (uint32_t)head[i]) & 0xffffu) >= CZK_WINDOW) head[i] = (uint16_t)((base - CZK_WINDOW) & 0xffffu);
+                    __syncwarp();
+                }
+                const uint32_t pos = base + lane;
+                const bool valid = pos + 4 <= n;
+                const uint32_t v = lds32u(chunk, pos - cb);
+                // lanes without 4 bytes left get a private pseudo-hash so they never group with real ones
+                const uint32_t h = valid ? hash4(v) : (0x10000u + lane);
+                const uint32_t grp = __match_any_sync(CZK_FULL, h);
+                uint32_t d = 0;
+                if (valid) {
+                    const uint32_t lower = grp & ((1u << lane) - 1u);
+                    if (lower) d = lane - (31u - (uint32_t)__clz((int)lower));  // nearest earlier lane with the same hash
+                    else {
+                        const uint32_t dd = (pos - (uint32_t)head[h]) & 0xffffu;
+                        if (dd >= 1 && dd < CZK_WINDOW && dd <= pos) d = dd;
+                    }
+                }
+                if (pos < n) pd[pos] = (uint16_t)d;
+                __syncwarp();
+                if (valid && (grp >> lane) <= 1u) head[h] = (uint16_t)(pos & 0xffffu);  // highest lane of the group
                 __syncwarp();
             }
-            const uint32_t pos = base + lane;
-            const bool valid = pos + 4 <= n;
-            const uint32_t v = v_next;
-            v_next = pos + 32 + 4 <= n ? load32u(s + pos + 32) : 0u;
-            // lanes without 4 bytes left get a private pseudo-hash so they never group with real ones
-            const uint32_t h = valid ? hash4(v) : (0x10000u + lane);
-            const uint32_t grp = __match_any_sync(CZK_FULL, h);
-            uint32_t d = 0;
-            if (valid) {
-                const uint32_t lower = grp & ((1u << lane) - 1u);
-                if (lower) d = lane - (31u - (uint32_t)__clz((int)lower));  // nearest earlier lane with the same hash
-                else {
-                    const uint32_t dd = (pos - (uint32_t)head[h]) & 0xffffu;
-                    if (dd >= 1 && dd < CZK_WINDOW && dd <= pos) d = dd;
-                }
-            }
-            if (pos < n) pd[pos] = (uint16_t)d;
-            __syncwarp();
-            if (valid && (grp >> lane) <= 1u) head[h] = (uint16_t)(pos & 0xffffu);  // highest lane of the group
-            __syncwarp();
         }
     }
 }
@@ -191,16 +222,146 @@ __global__ void __launch_bounds__(256) deflate_match_kernel(DeflateParams P, uin
     P.match[g] = P.tune.level0 ? 0u : find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune);
 }
 
+// ------------------------------------------------------------------ K2 (tiled)
+// The same search as find_match(), restructured for the machine (profiles/r1_deflate_match_v2_ncu.md: the simple
+// thread-per-position kernel runs with 12 of 32 lanes active and waits on L1/L2 for every link of the chain):
+//   * a CTA owns a tile of 4096 positions of ONE segment and stages the bytes and chain links it can reach
+//     (32 KiB back, 258 bytes ahead) in shared memory once: every chain step is a shared-memory access;
+//   * inside a warp the positions are handed out dynamically: each lane is a small state machine (IDLE -> CHAIN -> EXTEND)
+//     that does ONE step per loop iteration — examine one candidate, or compare one more word — so lanes whose chains are
+//     short pick up the next position instead of idling while their neighbours walk 16 links.
+// Candidate order, reject rules and tie-breaking are those of find_match(); the tests compare the outputs byte for byte.
+#define CZK_MT_POS 4096u                              // positions per tile
+#define CZK_MT_THREADS 256u
+#define CZK_MT_SPAN (CZK_WINDOW + CZK_MT_POS + 264u)  // bytes staged: window + tile + lookahead (258) + slack
+__device__ __forceinline__ uint32_t mt_tile_first(const DeflateParams &P, uint32_t seg) { return (uint32_t)(seg_base(P, seg) >> 12) + seg; }
+__host__ __device__ inline size_t deflate_match_tiled_smem() { return (size_t)CZK_MT_SPAN + 8 + 2 * (size_t)(CZK_WINDOW + CZK_MT_POS) + 16; }
+
+__global__ void __launch_bounds__(CZK_MT_THREADS) deflate_match_tiled_kernel(DeflateParams P) {
+    CZ_DYNAMIC_SMEM(smem_raw);
+    __shared__ uint32_t s_seg, s_tile, s_ok;
+    uint8_t *sb = smem_raw;                                                      // bytes  [w0, w0 + CZK_MT_SPAN)
+    uint16_t *sp = (uint16_t *)(smem_raw + ((CZK_MT_SPAN + 8 + 15) & ~15u));     // prevd  [w0, t1)
+    if (threadIdx.x == 0) {
+        uint32_t lo = 0, hi = P.nseg;  // last segment with mt_tile_first <= blockIdx.x
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (mt_tile_first(P, mid) <= blockIdx.x) lo = mid; else hi = mid;
+        }
+        s_seg = lo;
+        s_tile = blockIdx.x - mt_tile_first(P, lo);
+        s_ok = (uint64_t)s_tile * CZK_MT_POS < seg_len(P, lo);
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    const uint32_t seg = s_seg;
+    const uint32_t n = seg_len(P, seg);
+    const uint64_t base = seg_base(P, seg);
+    const uint8_t *src = P.in + P.seg_off[seg];
+    const uint16_t *pd = P.prevd + base;
+    uint32_t *mt = P.match + base;
+    const uint32_t t0 = s_tile * CZK_MT_POS;
+    const uint32_t t1 = t0 + CZK_MT_POS < n ? t0 + CZK_MT_POS : n;
+    const uint32_t w0 = t0 > CZK_WINDOW ? t0 - CZK_WINDOW : 0;
+    const uint32_t wb1 = t1 + 261 < n ? t1 + 261 : n;  // bytes staged: [w0, wb1)
+    for (uint32_t i = threadIdx.x; i < wb1 - w0; i += CZK_MT_THREADS) sb[i] = src[w0 + i];
+    for (uint32_t i = wb1 - w0 + threadIdx.x; i < wb1 - w0 + 8; i += CZK_MT_THREADS) sb[i] = 0;  // words read past the end
+    for (uint32_t i = threadIdx.x; i < t1 - w0; i += CZK_MT_THREADS) sp[i] = pd[w0 + i];
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // each warp owns a contiguous share of the tile and hands its positions out lane by lane
+    const uint32_t share = (t1 - t0 + 7) / 8;
+    uint32_t next = t0 + warp * share;
+    const uint32_t wend = next + share < t1 ? next + share : t1;
+    const uint32_t max_chain = P.tune.max_chain, nice_len = P.tune.nice_len;
+    enum { IDLE = 0, CHAIN = 1, EXTEND = 2 };
+    int state = IDLE;
+    uint32_t pos = 0, cur4 = 0, max_len = 0, best_len = 0, best_dist = 0, total = 0, d = 0, chain = 0, l = 0, nd = 0;
+    for (;;) {
+        // ---- hand out positions to idle lanes
+        const uint32_t idle = __ballot_sync(CZK_FULL, state == IDLE);
+        if (idle) {
+            const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
+            const uint32_t avail = next < wend ? wend - next : 0;
+            if (state == IDLE && rank < avail) {
+                pos = next + rank;
+                max_len = n - pos < CZK_MAX_MATCH ? n - pos : CZK_MAX_MATCH;
+                best_len = 0; best_dist = 0; total = 0;
+                d = max_len >= 4 ? sp[pos - w0] : 0;  // the last 3 positions of a segment have no link
+                chain = max_chain;
+                cur4 = lds32u(sb, pos - w0);
+                state = CHAIN;
+            }
+            const uint32_t taken = (uint32_t)__popc(idle) < avail ? (uint32_t)__popc(idle) : avail;
+            next += taken;
+            if (idle == CZK_FULL && taken == 0) break;  // nothing in flight and nothing left
+        }
+        // ---- one step per lane
+        bool finish = false;
+        if (state == CHAIN) {
+            if (!d || !chain) finish = true;
+            else {
+                chain--;
+                total += d;
+                if (total > CZK_WINDOW || total > pos) finish = true;
+                else {
+                    const uint32_t co = pos - total - w0;  // candidate, as an offset into the staged bytes
+                    nd = sp[co];
+                    bool take = lds32u(sb, co) == cur4;
+                    if (take && best_len >= 4 && best_len < max_len)
+                        take = lds32u(sb, co + best_len - 3) == lds32u(sb, pos - w0 + best_len - 3);
+                    if (take) { l = 4; state = EXTEND; }
+                    else d = nd;
+                }
+            }
+        } else if (state == EXTEND) {
+            const uint32_t co = pos - total - w0, po = pos - w0;
+            bool done = false;
+            if (l + 4 <= max_len) {
+                const uint32_t x = lds32u(sb, co + l) ^ lds32u(sb, po + l);
+                if (x) { l += ((uint32_t)__ffs((int)x) - 1u) >> 3; done = true; }
+                else l += 4;
+            } else {
+                // fewer than 4 bytes left: compare them in one masked word
+                const uint32_t rem = max_len - l;
+                uint32_t x = lds32u(sb, co + l) ^ lds32u(sb, po + l);
+                x &= rem ? (0xffffffffu >> (32 - 8 * rem)) : 0u;
+                l = x ? l + (((uint32_t)__ffs((int)x) - 1u) >> 3) : max_len;
+                done = true;
+            }
+            if (done) {
+                if (l > best_len) {
+                    best_len = l;
+                    best_dist = total;
+                    if (l >= nice_len || l == max_len) finish = true;
+                }
+                d = nd;
+                state = CHAIN;
+            }
+        }
+        if (finish) {
+            mt[pos] = best_len >= CZK_MIN_MATCH ? (best_len | (best_dist << 9)) : 0u;
+            state = IDLE;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ K3
-// One warp per segment. The parse itself is a serial chain (the next position depends on the match taken at this one), so
-// the warp stages a tile of positions in shared memory with coalesced loads, all lanes precompute "advance if a token
-// starts here" (match length, or 1 for a literal / a match deferred by the one-step lazy rule), ONE lane walks the tile
-// through shared memory marking token starts, and all lanes then emit the marked tokens with a popcount prefix.
+// One warp per segment. The parse is a serial chain (the next position depends on the match taken at this one). The warp
+// stages a tile of 2048 positions in shared memory with coalesced loads and all lanes precompute "advance if a token starts
+// here" (match length, or 1 for a literal / a match deferred by the one-step lazy rule). The chain itself is then walked
+// SPECULATIVELY: lane s walks sub-tile s (64 positions) from its first position, in parallel with the other lanes; parses
+// that start at different positions fall into step within a few tokens, so the true walk — sub-tile after sub-tile, entering
+// where the previous one left — only has to go until it meets a position the speculative walk also visited, and takes the
+// rest of that sub-tile (and its exit) from the speculation. All lanes then emit the marked tokens with a popcount prefix.
 // Same decisions as parse_segment() in deflate_core.cuh (the sequential statement the tests compare against).
 #define CZK_PARSE_TILE 2048u
+#define CZK_PARSE_SUB 64u
+__device__ __forceinline__ uint32_t parse_pad(uint32_t i) { return i + (i >> 6); }  // one pad entry per sub-tile: no bank conflicts
 __global__ void __launch_bounds__(32) deflate_parse_kernel(DeflateParams P) {
     __shared__ uint32_t raw_s[CZK_PARSE_TILE + 1];
-    __shared__ uint16_t adv_s[CZK_PARSE_TILE];
+    __shared__ uint16_t adv_s[CZK_PARSE_TILE + CZK_PARSE_TILE / CZK_PARSE_SUB];
     __shared__ uint32_t vis_s[CZK_PARSE_TILE / 32];
     const uint32_t lane = threadIdx.x;
     for (uint32_t seg = blockIdx.x; seg < P.nseg; seg += gridDim.x) {
@@ -215,31 +376,45 @@ __global__ void __launch_bounds__(32) deflate_parse_kernel(DeflateParams P) {
             const uint32_t T = n - t0 < CZK_PARSE_TILE ? n - t0 : CZK_PARSE_TILE;
             __syncwarp();
             for (uint32_t i = lane; i <= T; i += 32) raw_s[i] = t0 + i < n ? mt[t0 + i] : 0u;
-            if (lane < CZK_PARSE_TILE / 32) vis_s[lane] = 0;
-            for (uint32_t i = 32 + lane; i < CZK_PARSE_TILE / 32; i += 32) vis_s[i] = 0;
             __syncwarp();
             for (uint32_t i = lane; i < T; i += 32) {
                 const uint32_t len = raw_s[i] & 0x1ff;
                 const uint32_t nlen = (P.tune.lazy && t0 + i + 1 < n) ? (raw_s[i + 1] & 0x1ff) : 0;
-                adv_s[i] = (uint16_t)((len >= CZK_MIN_MATCH && !(nlen > len)) ? len : 1u);
+                adv_s[parse_pad(i)] = (uint16_t)((len >= CZK_MIN_MATCH && !(nlen > len)) ? len : 1u);
             }
             __syncwarp();
-            uint32_t p = entry;
-            if (lane == 0) {
-                while (p < T) {
-                    vis_s[p >> 5] |= 1u << (p & 31);
-                    p += adv_s[p];
+            // ---- speculative walk of sub-tile `lane` from its first position
+            const uint32_t s0 = lane * CZK_PARSE_SUB;                          // first position of my sub-tile
+            const uint32_t slen = s0 < T ? (T - s0 < CZK_PARSE_SUB ? T - s0 : CZK_PARSE_SUB) : 0;
+            unsigned long long m0 = 0;
+            uint32_t p = 0;
+            while (p < slen) { m0 |= 1ull << p; p += adv_s[parse_pad(s0 + p)]; }
+            const uint32_t exit0 = s0 + p;                                     // where the speculative walk leaves (tile-relative)
+            // ---- the true walk, sub-tile after sub-tile
+            unsigned long long fin = 0;
+            uint32_t cur = entry;
+            const uint32_t nsub = (T + CZK_PARSE_SUB - 1) / CZK_PARSE_SUB;
+            for (uint32_t s = 0; s < nsub; s++) {
+                uint32_t nxt = cur;
+                if (lane == s && cur < s0 + slen) {  // (cur >= s0 always: the walk never goes backwards)
+                    uint32_t q = cur - s0;
+                    unsigned long long pre = 0;
+                    while (q < slen && !((m0 >> q) & 1ull)) { pre |= 1ull << q; q += adv_s[parse_pad(s0 + q)]; }
+                    if (q < slen) { fin = pre | (m0 & ~((1ull << q) - 1ull)); nxt = exit0; }  // met the speculation: rest is identical
+                    else { fin = pre; nxt = s0 + q; }
                 }
+                cur = __shfl_sync(CZK_FULL, nxt, s);
             }
-            p = __shfl_sync(CZK_FULL, p, 0);
-            entry = p - T;
+            entry = cur - T;
+            vis_s[2 * lane] = (uint32_t)fin;
+            vis_s[2 * lane + 1] = (uint32_t)(fin >> 32);
             __syncwarp();
             for (uint32_t w = 0; w * 32 < T; w++) {
                 const uint32_t bits = vis_s[w];
                 if (bits >> lane & 1u) {
                     const uint32_t i = w * 32 + lane;
                     const uint32_t k = nt + (uint32_t)__popc(bits & ((1u << lane) - 1u));
-                    const uint32_t a = adv_s[i];
+                    const uint32_t a = adv_s[parse_pad(i)];
                     mt[k] = a == 1 ? (uint32_t)src[t0 + i] << 9 : raw_s[i];  // k <= t0 + i: never ahead of the tile being read
                     if ((k + 1) % CZK_BLOCK_TOKENS == 0) blk_end[(k + 1) / CZK_BLOCK_TOKENS - 1] = t0 + i + a;
                 }

@@ -164,9 +164,9 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
     CZ_CFG(16, 1); CZ_CFG(32, 1);
 #undef CZ_CFG
     // D = -2: two-phase, W = rounds per iteration of phase B (loads in flight per lane)
-    if (c.D == -2 && (c.W == 14 || c.W == 4)) return launch_two_phase<14, 8, 4>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && (c.W == 14 || c.W == 2)) return launch_two_phase<14, 8, 2>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
     if (c.D == -2 && c.W == 1) return launch_two_phase<14, 8, 1>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
-    if (c.D == -2 && c.W == 2) return launch_two_phase<14, 8, 2>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && c.W == 4) return launch_two_phase<14, 8, 4>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
     if (c.D == -2 && c.W == 8) return launch_two_phase<14, 8, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
     // D = -1: lane-per-stream canonical-decode kernel with W warps per CTA
     if (c.D == -1 && c.W == 14) return launch_lc<14>(st, ctx, P);

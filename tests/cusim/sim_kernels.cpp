@@ -81,9 +81,12 @@ extern "C" int sim_deflate(size_t nseg, size_t n_units, const uint8_t *in, const
     P.check_kind = unit_checks ? 3 : 0;
     cusim::set_seed(seed);
     const unsigned ns = P.nseg, nu = P.n_units, nsl = P.n_slots;
-    if (P.check_kind) cusim::launch((ns + 3) / 4, 128, 0, deflate_checksum_kernel, P);
+    if (P.check_kind) cusim::launch(ns < 3 ? ns : 3, 128, 0, deflate_checksum_kernel, P);
     if (!P.tune.level0 && !P.tune.huffman_only && !P.tune.rle_only) cusim::launch(ns < 3 ? ns : 3, 32, 0, deflate_chain_kernel, P);
-    cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_match_kernel, P, in_bytes);
+    if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || (seed & 2))
+        cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_match_kernel, P, in_bytes);
+    else
+        cusim::launch((unsigned)((in_bytes >> 12) + nseg + 1), CZK_MT_THREADS, deflate_match_tiled_smem(), deflate_match_tiled_kernel, P);
     cusim::launch(ns < 5 ? ns : 5, 32, 0, deflate_parse_kernel, P);
     cusim::launch(nsl, 128, 0, deflate_hist_kernel, P);
     cusim::launch((nsl + 31) / 32, 32, 0, deflate_plan_kernel, P);
