@@ -100,7 +100,7 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
         unsigned grid = nseg < (unsigned)ctx->sm_count * 12u ? nseg : (unsigned)ctx->sm_count * 12u;
         czk::deflate_chain_kernel<<<grid, 32, 0, st>>>(P);
     }
-    if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || getenv("CZ_MATCH_SIMPLE")) {
+    if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || !getenv("CZ_MATCH_TILED")) {
         czk::deflate_match_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
     } else {
         static bool configured[64] = {};

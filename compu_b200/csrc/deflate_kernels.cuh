@@ -225,6 +225,8 @@ __global__ void __launch_bounds__(256) deflate_match_kernel(DeflateParams P, uin
 // ------------------------------------------------------------------ K2 (tiled)
 // The same search as find_match(), restructured for the machine (profiles/r1_deflate_match_v2_ncu.md: the simple
 // thread-per-position kernel runs with 12 of 32 lanes active and waits on L1/L2 for every link of the chain):
+// (Measured, profiles/r1_deflate_notes.md: NOT faster than the simple kernel — the per-iteration vote and state bookkeeping
+// cost more than the idle lanes they save — so it is off by default; CZ_MATCH_TILED=1 selects it.)
 //   * a CTA owns a tile of 4096 positions of ONE segment and stages the bytes and chain links it can reach
 //     (32 KiB back, 258 bytes ahead) in shared memory once: every chain step is a shared-memory access;
 //   * inside a warp the positions are handed out dynamically: each lane is a small state machine (IDLE -> CHAIN -> EXTEND)
@@ -234,14 +236,13 @@ __global__ void __launch_bounds__(256) deflate_match_kernel(DeflateParams P, uin
 #define CZK_MT_POS 4096u                              // positions per tile
 #define CZK_MT_THREADS 256u
 #define CZK_MT_SPAN (CZK_WINDOW + CZK_MT_POS + 264u)  // bytes staged: window + tile + lookahead (258) + slack
+#define CZK_MT_SB_BYTES ((CZK_MT_SPAN + 16u + 32u + 15u) & ~15u)  // + alignment shift (16-byte vector loads) + zero tail
 __device__ __forceinline__ uint32_t mt_tile_first(const DeflateParams &P, uint32_t seg) { return (uint32_t)(seg_base(P, seg) >> 12) + seg; }
-__host__ __device__ inline size_t deflate_match_tiled_smem() { return (size_t)CZK_MT_SPAN + 8 + 2 * (size_t)(CZK_WINDOW + CZK_MT_POS) + 16; }
+__host__ __device__ inline size_t deflate_match_tiled_smem() { return (size_t)CZK_MT_SB_BYTES + 2 * (size_t)(CZK_WINDOW + CZK_MT_POS + 16); }
 
 __global__ void __launch_bounds__(CZK_MT_THREADS) deflate_match_tiled_kernel(DeflateParams P) {
     CZ_DYNAMIC_SMEM(smem_raw);
     __shared__ uint32_t s_seg, s_tile, s_ok;
-    uint8_t *sb = smem_raw;                                                      // bytes  [w0, w0 + CZK_MT_SPAN)
-    uint16_t *sp = (uint16_t *)(smem_raw + ((CZK_MT_SPAN + 8 + 15) & ~15u));     // prevd  [w0, t1)
     if (threadIdx.x == 0) {
         uint32_t lo = 0, hi = P.nseg;  // last segment with mt_tile_first <= blockIdx.x
         while (hi - lo > 1) {
@@ -264,9 +265,28 @@ __global__ void __launch_bounds__(CZK_MT_THREADS) deflate_match_tiled_kernel(Def
     const uint32_t t1 = t0 + CZK_MT_POS < n ? t0 + CZK_MT_POS : n;
     const uint32_t w0 = t0 > CZK_WINDOW ? t0 - CZK_WINDOW : 0;
     const uint32_t wb1 = t1 + 261 < n ? t1 + 261 : n;  // bytes staged: [w0, wb1)
-    for (uint32_t i = threadIdx.x; i < wb1 - w0; i += CZK_MT_THREADS) sb[i] = src[w0 + i];
-    for (uint32_t i = wb1 - w0 + threadIdx.x; i < wb1 - w0 + 8; i += CZK_MT_THREADS) sb[i] = 0;  // words read past the end
-    for (uint32_t i = threadIdx.x; i < t1 - w0; i += CZK_MT_THREADS) sp[i] = pd[w0 + i];
+    // 16-byte vector staging: the shared copies start at the enclosing 16-byte boundary of the global data, so position p is
+    // at sb[p - w0] with sb shifted by the misalignment (aligned vectors only touch words that hold at least one wanted byte)
+    const uint32_t mis_b = (uint32_t)((uintptr_t)(src + w0) & 15);
+    const uint32_t mis_p = (uint32_t)(((uintptr_t)(pd + w0) & 15) >> 1);
+    uint8_t *sb_raw = smem_raw;
+    uint16_t *sp_raw = (uint16_t *)(smem_raw + CZK_MT_SB_BYTES);
+    {
+        const uint4 *gb = (const uint4 *)(src + w0 - mis_b);
+        const uint32_t nvb = (wb1 - w0 + mis_b + 15) >> 4;
+        for (uint32_t i = threadIdx.x; i < nvb; i += CZK_MT_THREADS) ((uint4 *)sb_raw)[i] = gb[i];
+        const uint4 *gp = (const uint4 *)(pd + w0 - mis_p);
+        const uint32_t nvp = (t1 - w0 + mis_p + 7) >> 3;
+        for (uint32_t i = threadIdx.x; i < nvp; i += CZK_MT_THREADS) ((uint4 *)sp_raw)[i] = gp[i];
+        __syncthreads();
+        // bytes past the end of the segment must compare as "no match" deterministically: zero them (words are read 7 bytes ahead)
+        const uint32_t endb = wb1 - w0 + mis_b;
+        if (threadIdx.x < 32) sb_raw[endb + threadIdx.x] = 0;
+    }
+    // byte p of the segment sits at sb_raw[p - w0 + mis_b]; words are read from the ALIGNED base with the shift folded in
+    const uint8_t *sb = sb_raw;
+    const uint32_t bo = mis_b - w0;  // (wraps; only ever added to a position >= w0)
+    const uint16_t *sp = sp_raw + mis_p;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -279,44 +299,54 @@ __global__ void __launch_bounds__(CZK_MT_THREADS) deflate_match_tiled_kernel(Def
     int state = IDLE;
     uint32_t pos = 0, cur4 = 0, max_len = 0, best_len = 0, best_dist = 0, total = 0, d = 0, chain = 0, l = 0, nd = 0;
     for (;;) {
-        // ---- hand out positions to idle lanes
-        const uint32_t idle = __ballot_sync(CZK_FULL, state == IDLE);
-        if (idle) {
-            const uint32_t rank = __popc(idle & ((1u << lane) - 1u));
-            const uint32_t avail = next < wend ? wend - next : 0;
+        // ---- vote: run the phase most lanes are waiting for (every phase then executes with many lanes active)
+        const uint32_t m_idle = __ballot_sync(CZK_FULL, state == IDLE);
+        const uint32_t m_chain = __ballot_sync(CZK_FULL, state == CHAIN);
+        const uint32_t n_ext = 32u - (uint32_t)__popc(m_idle) - (uint32_t)__popc(m_chain);
+        const uint32_t avail = next < wend ? wend - next : 0;
+        const uint32_t n_new = (uint32_t)__popc(m_idle) < avail ? (uint32_t)__popc(m_idle) : avail;
+        const uint32_t n_chain = (uint32_t)__popc(m_chain);
+        if (!n_chain && !n_ext && !n_new) break;
+        if (n_new > n_chain && n_new >= n_ext) {
+            // ---- hand out positions to idle lanes
+            const uint32_t rank = __popc(m_idle & ((1u << lane) - 1u));
             if (state == IDLE && rank < avail) {
                 pos = next + rank;
                 max_len = n - pos < CZK_MAX_MATCH ? n - pos : CZK_MAX_MATCH;
                 best_len = 0; best_dist = 0; total = 0;
                 d = max_len >= 4 ? sp[pos - w0] : 0;  // the last 3 positions of a segment have no link
                 chain = max_chain;
-                cur4 = lds32u(sb, pos - w0);
+                cur4 = lds32u(sb, pos + bo);
                 state = CHAIN;
             }
-            const uint32_t taken = (uint32_t)__popc(idle) < avail ? (uint32_t)__popc(idle) : avail;
-            next += taken;
-            if (idle == CZK_FULL && taken == 0) break;  // nothing in flight and nothing left
-        }
-        // ---- one step per lane
-        bool finish = false;
-        if (state == CHAIN) {
-            if (!d || !chain) finish = true;
-            else {
-                chain--;
-                total += d;
-                if (total > CZK_WINDOW || total > pos) finish = true;
+            next += n_new;
+        } else if (n_chain >= n_ext) {
+            // ---- examine one candidate per lane
+            if (state == CHAIN) {
+                bool finish = false;
+                if (!d || !chain) finish = true;
                 else {
-                    const uint32_t co = pos - total - w0;  // candidate, as an offset into the staged bytes
-                    nd = sp[co];
-                    bool take = lds32u(sb, co) == cur4;
-                    if (take && best_len >= 4 && best_len < max_len)
-                        take = lds32u(sb, co + best_len - 3) == lds32u(sb, pos - w0 + best_len - 3);
-                    if (take) { l = 4; state = EXTEND; }
-                    else d = nd;
+                    chain--;
+                    total += d;
+                    if (total > CZK_WINDOW || total > pos) finish = true;
+                    else {
+                        const uint32_t cp = pos - total;  // candidate position
+                        nd = sp[cp - w0];
+                        bool take = lds32u(sb, cp + bo) == cur4;
+                        if (take && best_len >= 4 && best_len < max_len)
+                            take = lds32u(sb, cp + bo + best_len - 3) == lds32u(sb, pos + bo + best_len - 3);
+                        if (take) { l = 4; state = EXTEND; }
+                        else d = nd;
+                    }
+                }
+                if (finish) {
+                    mt[pos] = best_len >= CZK_MIN_MATCH ? (best_len | (best_dist << 9)) : 0u;
+                    state = IDLE;
                 }
             }
         } else if (state == EXTEND) {
-            const uint32_t co = pos - total - w0, po = pos - w0;
+            // ---- compare one more word per lane
+            const uint32_t co = pos - total + bo, po = pos + bo;
             bool done = false;
             if (l + 4 <= max_len) {
                 const uint32_t x = lds32u(sb, co + l) ^ lds32u(sb, po + l);
@@ -331,18 +361,17 @@ __global__ void __launch_bounds__(CZK_MT_THREADS) deflate_match_tiled_kernel(Def
                 done = true;
             }
             if (done) {
+                state = CHAIN;
+                d = nd;
                 if (l > best_len) {
                     best_len = l;
                     best_dist = total;
-                    if (l >= nice_len || l == max_len) finish = true;
+                    if (l >= nice_len || l == max_len) {  // good enough: stop searching
+                        mt[pos] = best_len | (best_dist << 9);
+                        state = IDLE;
+                    }
                 }
-                d = nd;
-                state = CHAIN;
             }
-        }
-        if (finish) {
-            mt[pos] = best_len >= CZK_MIN_MATCH ? (best_len | (best_dist << 9)) : 0u;
-            state = IDLE;
         }
     }
 }

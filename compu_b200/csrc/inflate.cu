@@ -86,6 +86,12 @@ uint64_t inflate_workspace_bytes(size_t n, uint64_t total_out_bytes) {
     return two_phase_tok_off(n) + 4 * (total_out_bytes + 8 * (uint64_t)n) + 256;
 }
 
+// Optional per-kernel timing of the two-phase path (bench.py: live CUDA-event durations of each kernel inside the timed region)
+static bool g_prof_on = false;
+struct ProfRec { cudaEvent_t e0, e1, e2; };
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+
 template <int WA, int WB, int H>
 static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams &P, void *d_ws, uint64_t ws_bytes,
                             uint64_t total_out_bytes, size_t n_span) {
@@ -114,13 +120,24 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
     }
     uint64_t ga = (P.n + 32 * WA - 1) / (32 * WA), gmax = (uint64_t)ctx->sm_count * per_sm_a[d];
     if (ga > gmax) ga = gmax;
+    ProfRec pr = {nullptr, nullptr, nullptr};
+    if (g_prof_on) {
+        cudaEventCreate(&pr.e0); cudaEventCreate(&pr.e1); cudaEventCreate(&pr.e2);
+        cudaEventRecord(pr.e0, st);
+    }
     ka<<<(unsigned)ga, WA * 32, smem, st>>>(Q);
+    if (g_prof_on) cudaEventRecord(pr.e1, st);
     uint64_t gb = (P.n + WB - 1) / WB;
     static int lz_cap = -1;  // experiment knob: CTAs of phase B per SM (fewer streams in flight => their windows fit L2)
     if (lz_cap < 0) { const char *e = getenv("CZ_LZ_CTAS_PER_SM"); lz_cap = e ? atoi(e) : 0; }
     gmax = (uint64_t)ctx->sm_count * (lz_cap > 0 && lz_cap < per_sm_b[d] ? lz_cap : per_sm_b[d]);
     if (gb > gmax) gb = gmax;
     kb<<<(unsigned)gb, WB * 32, 0, st>>>(Q);
+    if (g_prof_on) {
+        cudaEventRecord(pr.e2, st);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back(pr);
+    }
     return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
 }
 
@@ -219,4 +236,22 @@ extern "C" int cz_inflate_segments_device(void *cuda_stream, size_t n, const uin
     if (!ctx) return CZ_E_NO_DEVICE;
     return launch_inflate((cudaStream_t)cuda_stream, ctx, n, d_in, d_in_offsets, d_out, d_out_offsets, d_out_lens, d_statuses,
                           nullptr, d_checks, -15, 1, d_checks ? 3 : 0, d_workspace, workspace_bytes, total_out_bytes, nullptr, 0, 0);
+}
+
+extern "C" void cz_profile_enable(int on) { g_prof_on = on != 0; }
+
+extern "C" int cz_profile_read(double *ms_decode, double *ms_resolve) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    double a = 0, b = 0;
+    int k = 0;
+    for (ProfRec &r : g_prof) {
+        float x = 0, y = 0;
+        if (cudaEventSynchronize(r.e2) == cudaSuccess && cudaEventElapsedTime(&x, r.e0, r.e1) == cudaSuccess &&
+            cudaEventElapsedTime(&y, r.e1, r.e2) == cudaSuccess) { a += x; b += y; k++; }
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); cudaEventDestroy(r.e2);
+    }
+    g_prof.clear();
+    if (ms_decode) *ms_decode = a;
+    if (ms_resolve) *ms_resolve = b;
+    return k;
 }

@@ -152,6 +152,12 @@ int cz_inflate_segments_device(void *cuda_stream, size_t n, const uint8_t *d_in,
                                const uint64_t *d_out_offsets, uint64_t total_out_bytes, uint64_t *d_out_lens,
                                int32_t *d_statuses, uint32_t *d_checks, void *d_workspace, uint64_t workspace_bytes);
 
+/* Measurement hook: with profiling enabled every two-phase inflate launch records CUDA events around its two kernels on the
+   launching stream; cz_profile_read sums the durations (ms) of inflate_tok_kernel / inflate_lz_kernel over the launches since
+   the last read, waits for them, and returns the number of launches. */
+void cz_profile_enable(int on);
+int cz_profile_read(double *ms_decode, double *ms_resolve);
+
 /* Deflate on device. Unit i = d_in[in_offsets[i]..in_offsets[i+1]) is compressed as ONE raw full-flush segment (no header,
    no BFINAL, ends byte-aligned with 00 00 ff ff) into d_out[out_offsets[i]..]; d_out_lens[i] = bytes written (or needed, with
    d_statuses[i] = CZ_ENCODE_NEED_OUTPUT, when the slot is smaller), d_checks[2i], d_checks[2i+1] = adler32, crc32 of the
