@@ -14,7 +14,9 @@ namespace czk {
 #define CZK_WINDOW 32768u
 #define CZK_MIN_MATCH 3u
 #define CZK_MAX_MATCH 258u
+#ifndef CZK_HASH_BITS
 #define CZK_HASH_BITS 13
+#endif
 #define CZK_BLOCK_TOKENS 16384u   // tokens per deflate block (zlib memLevel 8: lit_bufsize)
 
 struct DeflateTuning {
@@ -80,6 +82,9 @@ __host__ __device__ inline uint32_t ctz32(uint32_t x) {
 // hash of the 4 bytes at p
 __host__ __device__ inline uint32_t hash4(uint32_t v) { return (v * 2654435761u) >> (32 - CZK_HASH_BITS); }
 
+#ifdef CZK_COUNT_STEPS
+static unsigned long long czk_step_count = 0;
+#endif
 // Best match for position `pos` of a segment: walk the chain of earlier positions with the same 4-byte hash
 // (prevd[i] = distance from i to the previous such position, 0 = none), newest first. Returns len | dist << 9, or 0.
 // Matches never cross the end of the segment and never look farther back than the segment start. A candidate must agree
@@ -102,6 +107,9 @@ __host__ __device__ inline uint32_t find_match(const uint8_t *seg, uint32_t seg_
     const uint32_t cur4 = load32u(cur);
     uint32_t total = 0, d = prevd[pos], chain = t.max_chain;
     while (d && chain--) {
+#ifdef CZK_COUNT_STEPS
+        czk_step_count++;
+#endif
         total += d;
         if (total > CZK_WINDOW || total > pos) break;
         const uint8_t *cand = cur - total;
@@ -119,6 +127,9 @@ __host__ __device__ inline uint32_t find_match(const uint8_t *seg, uint32_t seg_
                 best_len = l;
                 best_dist = total;
                 if (l >= t.nice_len || l == max_len) break;
+#ifdef CZK_GOOD_LEN  // experiment (tests/model sweeps): zlib's good_length rule
+                if (l >= CZK_GOOD_LEN) chain >>= 2;
+#endif
             }
         }
         d = prevd[pos - total];

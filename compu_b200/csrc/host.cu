@@ -180,7 +180,8 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
     }
     const size_t nsub = cut.size() - 1;
     // big units (megabytes in one stream) go to the warp-per-stream kernel, the rest to the two-phase path
-    const uint64_t big_in = 192u << 10, big_out = 1u << 20;
+    // (a lane decodes ~4 MB/s, a warp ~26 MB/s: beyond ~256 KiB of output the lane-per-stream path becomes the tail of the batch)
+    const uint64_t big_in = 96u << 10, big_out = 256u << 10;
     std::vector<uint32_t> ids;  // per sub-batch: [small ids..., big ids...], relative to the sub-batch's first unit
     std::vector<size_t> n_small(nsub, 0), n_big(nsub, 0), ids_at(nsub + 1, 0);
     bool any_big = false;

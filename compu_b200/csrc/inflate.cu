@@ -181,7 +181,16 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
     CZ_CFG(16, 1); CZ_CFG(32, 1);
 #undef CZ_CFG
     // D = -2: two-phase, W = rounds per iteration of phase B (loads in flight per lane)
-    if (c.D == -2 && (c.W == 14 || c.W == 2)) return launch_two_phase<14, 8, 2>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && (c.W == 14 || c.W == 0)) return launch_two_phase<14, 8, 0>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && c.W == 2) return launch_two_phase<14, 8, 2>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && c.W == -8) return launch_two_phase<14, 8, -8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && c.W == -12) return launch_two_phase<14, 8, -12>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && c.W == -24) return launch_two_phase<14, 8, -24>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && c.W == -32) return launch_two_phase<14, 8, -32>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -3 && c.W == 15) return launch_two_phase<15, 8, 0>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -3 && c.W == 13) return launch_two_phase<13, 8, 0>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -3 && c.W == 4) return launch_two_phase<14, 4, 0>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -3 && c.W == 16) return launch_two_phase<14, 16, 0>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
     if (c.D == -2 && c.W == 1) return launch_two_phase<14, 8, 1>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
     if (c.D == -2 && c.W == 4) return launch_two_phase<14, 8, 4>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
     if (c.D == -2 && c.W == 8) return launch_two_phase<14, 8, 8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);

@@ -50,6 +50,7 @@ __host__ __device__ inline uint64_t tok_word_off(uint64_t out_off, uint64_t unit
 
 #define CZK_TOK_LIT 0x80000000u
 #define CZK_TOK_STORED 0xC0000000u
+#define CZK_LZ_SHORT 12  // phase B (token-parallel): matches up to this long are copied by their own lane (8/12/16/24/32 measured: 33.9/32.6/34.0/35.5/38.0 ms)
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams Q) {
@@ -340,72 +341,143 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lz_kernel(TwoPhaseParams Q
                 }
                 const uint32_t total = __shfl_sync(CZK_FULL, pos, 31);
                 pos -= tl;
-                const uint64_t a0 = (uint64_t)(uintptr_t)ob + opos;   // absolute address of batch byte 0
-                int rel = -(int)(a0 & 31);                             // batch-relative index of this iteration's first byte
-                uint32_t cnt_before = 0;
-                uint8_t *obp = ob + opos;
-                // H sector-aligned 32-byte rounds per iteration. All back-reference loads of the iteration are issued before
-                // the first one is consumed (H loads in flight per lane: the kernel is bound by the latency of these
-                // loads, the windows of the streams in flight exceed L2); sources produced inside the iteration come from
-                // registers by shuffle.
-                for (; rel < (int)total; rel += 32 * H) {
-                    uint32_t val[H];
-                    int srcl[H], srch[H];  // source lane / source round inside this iteration (srch < 0: value is final)
-                    const int lo2 = rel > 0 ? rel : 0;
+                if constexpr (H <= 0) {
+                    constexpr int SHORT = H == 0 ? CZK_LZ_SHORT : -H;
+                    // ---- token-parallel resolution: lane = token. A token is copied by its own lane (literals; matches of up to
+                    // CZK_LZ_SHORT bytes that do not overlap themselves: all source bytes are loaded first, then stored) or by the
+                    // whole warp (long or self-overlapping matches). A match may read bytes that earlier tokens of this group
+                    // produce, so the group resolves in rounds: everything below the first unfinished token is complete, and a
+                    // token is ready when the part of this group it reads lies below that frontier.
+                    uint8_t *obp = ob + opos;
+                    const bool is_tok = lane < nt;
+                    const bool is_lit = is_tok && (t >> 31);
+                    const uint32_t dist = (t >> 9) & 0xffffu;
+                    const int ipos = (int)pos;
+                    const int src0 = ipos - (int)dist;
+                    int dep_end = 0;  // bytes of THIS group the token reads end here (exclusive); <= 0: none
+                    if (is_tok && !is_lit) { dep_end = src0 + (int)tl; if (dep_end > ipos) dep_end = ipos; }
+                    const bool coop = is_tok && !is_lit && (tl > (uint32_t)SHORT || dist < tl);
+                    bool done = !is_tok;
+                    for (;;) {
+                        const uint32_t undone = __ballot_sync(CZK_FULL, !done);
+                        if (!undone) break;
+                        const int first = __ffs((int)undone) - 1;
+                        const int frontier = __shfl_sync(CZK_FULL, ipos, first);
+                        const bool ready = !done && dep_end <= frontier;  // (always true for the first unfinished token)
+                        if (ready && !coop) {
+                            uint8_t *d = obp + ipos;
+                            if (is_lit) {
+                                d[0] = (uint8_t)t;
+                                if (tl > 1) d[1] = (uint8_t)(t >> 8);
+                                if (tl > 2) d[2] = (uint8_t)(t >> 16);
+                            } else {
+                                const uint8_t *sp = obp + src0;
+                                uint32_t bb[SHORT];
 #pragma unroll
-                    for (int h = 0; h < H; h++) {
-                        const int r0 = rel + 32 * h;
-                        // which tokens start inside this round? (every token covers at least one byte)
-                        uint32_t bit = (lane < nt && (int)pos >= r0 && (int)pos < r0 + 32) ? 1u << ((int)pos - r0) : 0u;
-                        uint32_t S = __reduce_or_sync(CZK_FULL, bit);
-                        const int j = r0 + (int)lane;
-                        const bool active = j >= 0 && j < (int)total;
-                        // lane holding the token that covers byte j
-                        int src_lane = (int)cnt_before + __popc(S & (0xffffffffu >> (31 - lane))) - 1;
-                        cnt_before += __popc(S);
-                        uint32_t tk = __shfl_sync(CZK_FULL, t, src_lane & 31);
-                        uint32_t tpp = __shfl_sync(CZK_FULL, pos, src_lane & 31);
-                        val[h] = 0; srcl[h] = 0; srch[h] = -1;
-                        if (active) {
-                            uint32_t off = (uint32_t)j - tpp;
-                            if (tk >> 31) val[h] = (tk >> (8 * off)) & 0xff;
-                            else {
-                                uint32_t dist = (tk >> 9) & 0xffffu;
-                                if (off >= dist) {  // overlapping copy: off mod dist without the integer-division sequence (off < 512)
-                                    uint32_t q = (uint32_t)__float2uint_rz(__fdividef((float)off, (float)dist));
-                                    uint32_t r = off - q * dist;
-                                    if ((int)r < 0) r += dist;
-                                    if (r >= dist) r -= dist;
-                                    off = r;
-                                }
-                                int src = (int)tpp - (int)dist + (int)off;  // batch-relative source index (< tpp)
-                                if (src >= lo2) { srch[h] = (src - rel) >> 5; srcl[h] = (src - rel) & 31; }
-                                else val[h] = obp[src];                     // bytes of earlier iterations / batches
+                                for (int k = 0; k < SHORT; k++) bb[k] = k < (int)tl ? sp[k] : 0u;
+#pragma unroll
+                                for (int k = 0; k < SHORT; k++) if (k < (int)tl) d[k] = (uint8_t)bb[k];
                             }
                         }
-                    }
-#pragma unroll
-                    for (int h = 0; h < H; h++) {
-#pragma unroll
-                        for (int hp = 0; hp < h; hp++) {  // sources in earlier rounds of this iteration: already final
-                            uint32_t v = __shfl_sync(CZK_FULL, val[hp], srcl[h]);
-                            if (srch[h] == hp) { val[h] = v; srch[h] = -1; }
+                        uint32_t cm = __ballot_sync(CZK_FULL, ready && coop);
+                        while (cm) {
+                            const int sl = __ffs((int)cm) - 1;
+                            cm &= cm - 1;
+                            const uint32_t Ln = __shfl_sync(CZK_FULL, tl, sl), D = __shfl_sync(CZK_FULL, dist, sl);
+                            const int P0 = __shfl_sync(CZK_FULL, ipos, sl);
+                            uint8_t *d = obp + P0;
+                            const uint8_t *sp = d - D;  // bytes [P0 - D, P0) are complete
+                            if (D >= Ln) {
+                                for (uint32_t k = lane; k < Ln; k += 32) d[k] = sp[k];
+                            } else if (D >= 32) {
+                                // overlapping, but a 32-byte step only reads what earlier steps wrote
+                                for (uint32_t k0 = 0; k0 < Ln; k0 += 32) {
+                                    const uint32_t k = k0 + lane;
+                                    if (k < Ln) d[k] = sp[k];
+                                    __syncwarp();
+                                }
+                            } else {
+                                // short period: byte k repeats source byte k mod D (incremental modulo)
+                                uint32_t r = lane % D;
+                                const uint32_t stepD = 32u % D;
+                                for (uint32_t k = lane; k < Ln; k += 32) {
+                                    d[k] = sp[r];
+                                    r += stepD;
+                                    if (r >= D) r -= D;
+                                }
+                            }
                         }
-                        bool need = srch[h] == h;
-                        uint32_t pend = __ballot_sync(CZK_FULL, need);
-                        while (pend) {
-                            uint32_t v = __shfl_sync(CZK_FULL, val[h], srcl[h]);
-                            bool src_ready = !((pend >> srcl[h]) & 1u);
-                            if (need && src_ready) { val[h] = v; need = false; }
-                            pend = __ballot_sync(CZK_FULL, need);
+                        done = done || ready;
+                        __syncwarp();
+                    }
+                } else {
+                    const uint64_t a0 = (uint64_t)(uintptr_t)ob + opos;   // absolute address of batch byte 0
+                    int rel = -(int)(a0 & 31);                             // batch-relative index of this iteration's first byte
+                    uint32_t cnt_before = 0;
+                    uint8_t *obp = ob + opos;
+                    // H sector-aligned 32-byte rounds per iteration. All back-reference loads of the iteration are issued before
+                    // the first one is consumed (H loads in flight per lane: the kernel is bound by the latency of these
+                    // loads, the windows of the streams in flight exceed L2); sources produced inside the iteration come from
+                    // registers by shuffle.
+                    for (; rel < (int)total; rel += 32 * H) {
+                        uint32_t val[H];
+                        int srcl[H], srch[H];  // source lane / source round inside this iteration (srch < 0: value is final)
+                        const int lo2 = rel > 0 ? rel : 0;
+    #pragma unroll
+                        for (int h = 0; h < H; h++) {
+                            const int r0 = rel + 32 * h;
+                            // which tokens start inside this round? (every token covers at least one byte)
+                            uint32_t bit = (lane < nt && (int)pos >= r0 && (int)pos < r0 + 32) ? 1u << ((int)pos - r0) : 0u;
+                            uint32_t S = __reduce_or_sync(CZK_FULL, bit);
+                            const int j = r0 + (int)lane;
+                            const bool active = j >= 0 && j < (int)total;
+                            // lane holding the token that covers byte j
+                            int src_lane = (int)cnt_before + __popc(S & (0xffffffffu >> (31 - lane))) - 1;
+                            cnt_before += __popc(S);
+                            uint32_t tk = __shfl_sync(CZK_FULL, t, src_lane & 31);
+                            uint32_t tpp = __shfl_sync(CZK_FULL, pos, src_lane & 31);
+                            val[h] = 0; srcl[h] = 0; srch[h] = -1;
+                            if (active) {
+                                uint32_t off = (uint32_t)j - tpp;
+                                if (tk >> 31) val[h] = (tk >> (8 * off)) & 0xff;
+                                else {
+                                    uint32_t dist = (tk >> 9) & 0xffffu;
+                                    if (off >= dist) {  // overlapping copy: off mod dist without the integer-division sequence (off < 512)
+                                        uint32_t q = (uint32_t)__float2uint_rz(__fdividef((float)off, (float)dist));
+                                        uint32_t r = off - q * dist;
+                                        if ((int)r < 0) r += dist;
+                                        if (r >= dist) r -= dist;
+                                        off = r;
+                                    }
+                                    int src = (int)tpp - (int)dist + (int)off;  // batch-relative source index (< tpp)
+                                    if (src >= lo2) { srch[h] = (src - rel) >> 5; srcl[h] = (src - rel) & 31; }
+                                    else val[h] = obp[src];                     // bytes of earlier iterations / batches
+                                }
+                            }
                         }
+    #pragma unroll
+                        for (int h = 0; h < H; h++) {
+    #pragma unroll
+                            for (int hp = 0; hp < h; hp++) {  // sources in earlier rounds of this iteration: already final
+                                uint32_t v = __shfl_sync(CZK_FULL, val[hp], srcl[h]);
+                                if (srch[h] == hp) { val[h] = v; srch[h] = -1; }
+                            }
+                            bool need = srch[h] == h;
+                            uint32_t pend = __ballot_sync(CZK_FULL, need);
+                            while (pend) {
+                                uint32_t v = __shfl_sync(CZK_FULL, val[h], srcl[h]);
+                                bool src_ready = !((pend >> srcl[h]) & 1u);
+                                if (need && src_ready) { val[h] = v; need = false; }
+                                pend = __ballot_sync(CZK_FULL, need);
+                            }
+                        }
+    #pragma unroll
+                        for (int h = 0; h < H; h++) {
+                            const int j = rel + 32 * h + (int)lane;
+                            if (j >= 0 && j < (int)total) obp[j] = (uint8_t)val[h];
+                        }
+                        __syncwarp();
                     }
-#pragma unroll
-                    for (int h = 0; h < H; h++) {
-                        const int j = rel + 32 * h + (int)lane;
-                        if (j >= 0 && j < (int)total) obp[j] = (uint8_t)val[h];
-                    }
-                    __syncwarp();
                 }
                 opos += total;
                 ti += nt;

@@ -32,7 +32,8 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
         case 8: run_inflate<8, 1>(P, grid); break;
         case 32: run_inflate<32, 1>(P, grid); break;
         case -1: cusim::launch(grid, 2 * 32, inflate_lc_smem_bytes<2>(), inflate_lc_kernel<2>, P); break;
-        case -2: {
+        case -2:
+        case -3: {
             const uint64_t total_out = out_off[n] - out_off[0];
             std::vector<uint32_t> tok(total_out + 8 * n + 64, 0xDEADBEEFu);
             std::vector<TokMeta> meta(n);
@@ -40,8 +41,10 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
             TwoPhaseParams Q;
             Q.base = P; Q.tok = tok.data(); Q.meta = meta.data(); Q.counter_b = &counter_b;
             cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2>, Q);
-            if (seed & 1) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 4>, Q);
-            else cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 2>, Q);
+            if (D == -3) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 0>, Q);
+            else if (seed % 3 == 0) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 4>, Q);
+            else if (seed % 3 == 1) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 2>, Q);
+            else cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 0>, Q);
             for (size_t i = total_out + 8 * n; i < tok.size(); i++) if (tok[i] != 0xDEADBEEFu) return -2;  // token area overrun
             break;
         }

@@ -1,6 +1,7 @@
 // deflate_model.cpp — sequential host run of the encoder's decisions (TEST INFRASTRUCTURE, not the product).
 // Compiles compu_b200/csrc/deflate_core.cuh for the host and strings the passes together one after another, so that the
 // CUDA kernels' output can be compared byte for byte, and so that ratio tuning does not need a GPU.
+#define CZK_COUNT_STEPS
 #define __host__
 #define __device__
 #include <stdint.h>
@@ -105,7 +106,7 @@ extern "C" long model_deflate_segment(const uint8_t *seg, uint32_t n, uint8_t *o
     bw.align();
     bw.put(0, 16);
     bw.put(0xffff, 16);
-    if (stats) { stats[0] = nt; stats[1] = n_lit; stats[2] = n_match; stats[3] = nb; stats[4] = types[0]; stats[5] = types[1]; stats[6] = types[2]; }
+    if (stats) { stats[0] = nt; stats[1] = n_lit; stats[2] = n_match; stats[3] = nb; stats[4] = types[0]; stats[5] = types[1]; stats[6] = types[2]; stats[7] = czk_step_count; czk_step_count = 0; }
     if (bw.overflow) return -1;
     return (long)(bw.nbits >> 3);
 }
