@@ -158,7 +158,7 @@ static uint64_t inflate_sub_batch_bytes() {
 // hold this shard. Everything is enqueued; the caller waits with InflateWork::sync_all().
 static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const uint8_t *in, const uint64_t *in_off, uint8_t *out,
                          const uint64_t *out_off, uint64_t *out_lens, int32_t *statuses, uint64_t *in_consumed,
-                         int window_bits, int segment_mode, uint32_t *checks) {
+                         int window_bits, int segment_mode, uint32_t *checks, const uint8_t *skip) {
     DeviceCtx *ctx = device_ctx(dev);
     if (!ctx) return CZ_E_NO_DEVICE;
     if (!CZ_CUDA(cudaSetDevice(dev)) || !w.init(dev)) return CZ_E_MEM;
@@ -190,6 +190,7 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
         for (int pass = 0; pass < 2; pass++)
             for (size_t i = cut[k]; i < cut[k + 1]; i++) {
                 const bool big = in_off[u0 + i + 1] - in_off[u0 + i] > big_in || out_off[u0 + i + 1] - out_off[u0 + i] > big_out;
+                if (skip && skip[u0 + i]) { any_big = true; continue; }  // already decoded (speculative split): in neither list
                 if ((int)big == pass) { ids.push_back((uint32_t)(i - cut[k])); (big ? n_big[k] : n_small[k])++; any_big |= big; }
             }
     }
@@ -255,6 +256,202 @@ static void split_by_bytes(size_t n, const uint64_t *off, int parts, std::vector
     cuts[parts] = n;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Speculative split of ONE long stream. A DEFLATE stream is serial for a decoder lane (a warp manages ~26 MB/s), but streams
+// written with full-flush points — ours (header | segment* | 03 00 | trailer), pigz's, anything using Z_FULL_FLUSH — can be
+// cut after every `00 00 ff ff` marker and the pieces decoded independently. Nothing in the stream says which markers are
+// real, so every step is verified instead of assumed:
+//   1. candidate cuts = occurrences of 00 00 ff ff (thinned to pieces of >= 256 KiB);
+//   2. COUNT pass (phase A of the two-phase kernel, no output): piece j decoded as a history-free raw fragment must end
+//      exactly at the next cut at a block boundary (=> the cut IS a block boundary) and must never reference bytes before
+//      its own start (=> no history crosses the cut). A failing piece is merged with its neighbours and recounted;
+//   3. with every piece verified and sized, the pieces are decoded in parallel into their final places with per-piece
+//      Adler-32 / CRC-32, the values are folded with the combine identities and compared with the container trailer.
+// If the stream does not split (sync-flush only, no markers, too many failures) the caller decodes it serially.
+struct CountWork {
+    DevBuf in, meta;
+    cudaStream_t stream = nullptr;
+    int dev = -1;
+    bool init(int d) {
+        if (dev == d && stream) return true;
+        dev = d;
+        return CZ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    }
+};
+
+struct CountMeta {  // == czk::TokMeta (inflate_two_phase.cuh)
+    uint32_t ntok;
+    int32_t status;
+    uint64_t out_len;
+    uint32_t expect, wrap;
+};
+
+// sizes / statuses / consumed bytes of the pieces [in_off[j], in_off[j+1]) of `in`; dev_in_valid: the device copy is current
+static int inflate_count_host(CountWork &w, int dev, const uint8_t *in, uint64_t in_bytes, bool &dev_in_valid, size_t n,
+                              const uint64_t *in_off, int window_bits, int segment_mode, uint64_t *out_lens, int32_t *statuses,
+                              uint64_t *consumed) {
+    DeviceCtx *ctx = device_ctx(dev);
+    if (!ctx) return CZ_E_NO_DEVICE;
+    if (!CZ_CUDA(cudaSetDevice(dev)) || !w.init(dev)) return CZ_E_MEM;
+    // meta: in_off[n+1] caps[n+1] consumed[n] | ws: counter 256 + CountMeta[n]
+    const size_t m_cap = 8 * (n + 1), m_cons = m_cap + 8 * (n + 1), m_ws = align_up(m_cons + 8 * n, 256),
+                 m_total = m_ws + 256 + sizeof(CountMeta) * n;
+    if (!w.in.reserve(in_bytes + 16) || !w.meta.reserve(m_total)) return CZ_E_MEM;
+    std::vector<uint64_t> h(2 * (n + 1));
+    for (size_t i = 0; i <= n; i++) { h[i] = in_off[i]; h[n + 1 + i] = (uint64_t)i << 40; }  // "unlimited" output slots
+    uint8_t *dm = w.meta.as<uint8_t>();
+    cudaStream_t st = w.stream;
+    if (!dev_in_valid && in_bytes && !CZ_CUDA(cudaMemcpyAsync(w.in.p, in, in_bytes, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
+    dev_in_valid = true;
+    if (!CZ_CUDA(cudaMemcpyAsync(dm, h.data(), 16 * (n + 1), cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
+    void *d_meta = nullptr;
+    int rc = launch_inflate_count(st, ctx, n, w.in.as<uint8_t>(), (const uint64_t *)dm, (const uint64_t *)(dm + m_cap),
+                                  (uint64_t *)(dm + m_cons), window_bits, segment_mode, dm + m_ws, 256 + sizeof(CountMeta) * n, &d_meta);
+    if (rc) return rc;
+    std::vector<CountMeta> hm(n);
+    if (!CZ_CUDA(cudaMemcpyAsync(hm.data(), d_meta, sizeof(CountMeta) * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+    if (!CZ_CUDA(cudaMemcpyAsync(consumed, dm + m_cons, 8 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+    if (!CZ_CUDA(cudaStreamSynchronize(st))) return CZ_E_MEM;
+    for (size_t i = 0; i < n; i++) { out_lens[i] = hm[i].out_len; statuses[i] = hm[i].status; }
+    return 0;
+}
+
+// bytes of container header at the start of `p` (0 = raw), or -1 if it is not a complete, plain header
+static long host_header_len(const uint8_t *p, uint64_t n, int window_bits, int &wrap) {
+    wrap = window_bits < 0 ? 0 : window_bits == 15 ? 1 : window_bits == 31 ? 2 : (n >= 2 && p[0] == 0x1f && p[1] == 0x8b) ? 2 : 1;
+    if (wrap == 0) return 0;
+    if (wrap == 1) {
+        if (n < 2 || (p[0] & 0x0f) != 8 || (p[0] >> 4) > 7 || ((p[0] << 8 | p[1]) % 31) || (p[1] & 0x20)) return -1;
+        return 2;
+    }
+    if (n < 10 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || (p[3] & 0xe0)) return -1;
+    uint64_t o = 10;
+    const int flg = p[3];
+    if (flg & 4) { if (o + 2 > n) return -1; o += 2 + (p[o] | p[o + 1] << 8); }
+    if (flg & 8) { while (o < n && p[o]) o++; o++; }
+    if (flg & 16) { while (o < n && p[o]) o++; o++; }
+    if (flg & 2) o += 2;  // FHCRC: verified only by the serial path; a wrong value still fails there... so refuse
+    if (flg & 2) return -1;
+    return o <= n ? (long)o : -1;
+}
+
+static uint64_t huge_unit_bytes() {
+    static uint64_t v = 0;
+    if (!v) {
+        v = 2ull << 20;
+        if (const char *e = getenv("CZ_SPLIT_MIN_KB")) { long k = atol(e); if (k >= 1) v = (uint64_t)k << 10; }
+    }
+    return v;
+}
+
+// true: the unit was decoded (results written). false: not splittable / does not fit — decode it the ordinary way.
+static bool inflate_split_speculative(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t cap, int window_bits,
+                                      uint32_t devices_mask, uint64_t *out_len, int32_t *status, uint64_t *consumed) {
+    int wrap = 0;
+    const long hl = host_header_len(in, in_len, window_bits, wrap);
+    if (hl < 0) return false;
+    // 1. candidate cuts
+    static const uint8_t mark[4] = {0x00, 0x00, 0xff, 0xff};
+    std::vector<uint64_t> cut;
+    cut.push_back((uint64_t)hl);
+    {
+        const uint64_t min_piece = 256u << 10;
+        uint64_t from = (uint64_t)hl;
+        while (from + 4 <= in_len) {
+            const uint8_t *m = (const uint8_t *)memmem(in + from, in_len - from, mark, 4);
+            if (!m) break;
+            const uint64_t c = (uint64_t)(m - in) + 4;
+            if (c - cut.back() >= min_piece) cut.push_back(c);
+            from = (uint64_t)(m - in) + 1;
+        }
+    }
+    if (cut.size() < 3) return false;  // fewer than two verified-able pieces: nothing to gain
+    const int dev = devices_mask ? __builtin_ctz(devices_mask) : 0;
+    static thread_local CountWork cw;
+    bool dev_in_valid = false;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    // 2. count + verify, merging pieces around cuts that do not verify
+    std::vector<uint64_t> lens, cons;
+    std::vector<int32_t> st;
+    uint64_t tail_len = 0, tail_cons = 0;
+    int32_t tail_st = 0;
+    bool ok = false;
+    for (int iter = 0; iter < 4; iter++) {
+        const size_t np = cut.size() - 1;  // pieces [cut[j], cut[j+1]); the tail [cut[np], in_len) holds the final block
+        lens.assign(np, 0); cons.assign(np, 0); st.assign(np, 0);
+        if (inflate_count_host(cw, dev, in, in_len, dev_in_valid, np, cut.data(), -15, 1, lens.data(), st.data(), cons.data())) break;
+        const uint64_t toff[2] = {cut[np], in_len};
+        if (inflate_count_host(cw, dev, in, in_len, dev_in_valid, 1, toff, -15, 0, &tail_len, &tail_st, &tail_cons)) break;
+        if (tail_st != CZ_DECODE_FINISHED) break;  // the end of the stream is not where the last cut says: not ours to split
+        // a false cut makes BOTH pieces around it fail (the one before runs out of input mid-block, the one after starts on
+        // garbage), so a failing piece loses its start and its end cut; true cuts lost that way only make pieces coarser
+        std::vector<uint8_t> bad_piece(np, 0);
+        size_t bad = 0;
+        for (size_t j = 0; j < np; j++)
+            if (!(st[j] == CZ_DECODE_FINISHED && cons[j] == cut[j + 1] - cut[j])) { bad_piece[j] = 1; bad++; }
+        if (bad == 0) { ok = true; break; }
+        if (bad * 4 > np) break;  // mostly failures: sync-flush points (history crosses them), not full-flush ones
+        std::vector<uint64_t> keep;
+        keep.push_back(cut[0]);
+        for (size_t k = 1; k < np; k++)
+            if (!bad_piece[k - 1] && !bad_piece[k]) keep.push_back(cut[k]);
+        keep.push_back(cut[np]);
+        if (keep.size() < 3) break;
+        cut.swap(keep);
+    }
+    cudaSetDevice(prev);
+    if (!ok) return false;
+    const size_t np = cut.size() - 1;
+    uint64_t total = tail_len;
+    for (size_t j = 0; j < np; j++) total += lens[j];
+    if (total > cap) return false;  // the ordinary path reports NeedOutput with the exact partial output
+    // 3. decode the verified pieces in parallel, straight into place
+    std::vector<uint64_t> in_off(cut), out_off(np + 2, 0), got(np + 1, 0);
+    in_off.push_back(in_len);  // piece np = the tail
+    for (size_t j = 0; j < np; j++) out_off[j + 1] = out_off[j] + lens[j];
+    out_off[np + 1] = out_off[np] + tail_len;
+    std::vector<int32_t> pst(np + 1, 0);
+    std::vector<uint32_t> chk(2 * (np + 1), 0);
+    std::vector<uint64_t> pcons(np + 1, 0);
+    if (inflate_batch_host(np, in, in_off.data(), out, out_off.data(), got.data(), pst.data(), nullptr, -15, 1, chk.data(), devices_mask))
+        return false;
+    if (inflate_batch_host(1, in, in_off.data() + np, out, out_off.data() + np, got.data() + np, pst.data() + np, pcons.data() + np, -15,
+                           0, chk.data() + 2 * np, devices_mask))
+        return false;
+    uint32_t adler = 1, crc = 0;
+    for (size_t j = 0; j <= np; j++) {
+        if (pst[j] != CZ_DECODE_FINISHED || got[j] != out_off[j + 1] - out_off[j]) return false;  // (cannot happen after the count pass)
+        adler = czk::adler32_combine_u(adler, chk[2 * j], got[j]);
+        crc = czk::crc32_combine_u(crc, chk[2 * j + 1], got[j]);
+    }
+    // container trailer right after the final block
+    uint64_t end = cut[np] + pcons[np];
+    int32_t fin = CZ_DECODE_FINISHED;
+    if (wrap == 1) {
+        if (end + 4 > in_len) fin = CZ_DECODE_NEED_INPUT;
+        else {
+            const uint8_t *t = in + end;
+            if (((uint32_t)t[0] << 24 | (uint32_t)t[1] << 16 | (uint32_t)t[2] << 8 | t[3]) != adler) fin = CZ_E_DATA;
+            end += 4;
+        }
+    } else if (wrap == 2) {
+        if (end + 8 > in_len) fin = CZ_DECODE_NEED_INPUT;
+        else {
+            const uint8_t *t = in + end;
+            const uint32_t c = (uint32_t)t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
+            const uint32_t isz = (uint32_t)t[4] | (uint32_t)t[5] << 8 | (uint32_t)t[6] << 16 | (uint32_t)t[7] << 24;
+            if (c != crc || isz != (uint32_t)total) fin = CZ_E_DATA;
+            end += 8;
+        }
+    }
+    if (fin == CZ_DECODE_NEED_INPUT) end = in_len;
+    *out_len = total;
+    *status = fin;
+    if (consumed) *consumed = end;
+    return true;
+}
+
 int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint8_t *out, const uint64_t *out_off,
                        uint64_t *out_lens, int32_t *statuses, uint64_t *in_consumed, int window_bits, int segment_mode,
                        uint32_t *checks, uint32_t devices_mask) {
@@ -265,6 +462,22 @@ int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint
         if (devices_mask >> d & 1) devs.push_back(d);
     for (int d : devs)
         if (!device_ctx(d)) return CZ_E_NO_DEVICE;
+    // long single streams first: split speculatively at full-flush markers where that verifies (see above)
+    std::vector<uint8_t> skip;
+    struct Done { size_t i; uint64_t len, cons; int32_t st; };
+    std::vector<Done> done;
+    if (!segment_mode && !checks && !getenv("CZ_NO_SPLIT")) {
+        for (size_t i = 0; i < n; i++) {
+            if (in_off[i + 1] - in_off[i] < huge_unit_bytes()) continue;
+            Done d{i, 0, 0, 0};
+            if (inflate_split_speculative(in + in_off[i], in_off[i + 1] - in_off[i], out + out_off[i], out_off[i + 1] - out_off[i],
+                                          window_bits, devices_mask, &d.len, &d.st, &d.cons)) {
+                if (skip.empty()) skip.assign(n, 0);
+                skip[i] = 1;
+                done.push_back(d);
+            }
+        }
+    }
     static thread_local InflateWork works[32];
     int prev = 0;
     cudaGetDevice(&prev);
@@ -274,7 +487,7 @@ int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint
     // enqueue every shard first (copies and kernels of different devices overlap), then wait for all
     for (size_t k = 0; k < devs.size() && !rc; k++)
         rc = inflate_shard(works[devs[k]], devs[k], cuts[k], cuts[k + 1], in, in_off, out, out_off, out_lens, statuses,
-                           in_consumed, window_bits, segment_mode, checks);
+                           in_consumed, window_bits, segment_mode, checks, skip.empty() ? nullptr : skip.data());
     for (size_t k = 0; k < devs.size(); k++) {
         if (!works[devs[k]].streams[0]) continue;
         cudaSetDevice(devs[k]);
@@ -287,6 +500,11 @@ int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint
             if (checks) memcpy(checks + 2 * w.res_u0, w.res_chk, 8 * w.res_n);
         }
         w.res_n = 0;
+    }
+    for (const Done &d : done) {
+        out_lens[d.i] = d.len;
+        statuses[d.i] = d.st;
+        if (in_consumed) in_consumed[d.i] = d.cons;
     }
     cudaSetDevice(prev);
     return rc;

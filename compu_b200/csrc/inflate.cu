@@ -102,6 +102,7 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
     }
     czk::TwoPhaseParams Q;
     Q.base = P;
+    Q.count_only = 0;
     Q.counter_b = (unsigned long long *)((uint8_t *)d_ws + 128);
     Q.meta = (czk::TokMeta *)((uint8_t *)d_ws + two_phase_meta_off());
     Q.tok = (uint32_t *)((uint8_t *)d_ws + two_phase_tok_off(n_span));
@@ -138,6 +139,42 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
         std::lock_guard<std::mutex> lk(g_prof_mu);
         g_prof.push_back(pr);
     }
+    return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
+}
+
+
+// Phase A alone in counting mode: output size, status and consumed bytes of every unit, nothing written but TokMeta.
+// Workspace: [counter 256 B][TokMeta n]. The caller reads the TokMeta array (device pointer returned) after the stream.
+int launch_inflate_count(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
+                         const uint64_t *d_out_off, uint64_t *d_in_consumed, int window_bits, int segment_mode, void *d_ws,
+                         uint64_t ws_bytes, void **d_meta_ret) {
+    if (n == 0) return 0;
+    if (n > 0xfffffff0u || !d_ws || ws_bytes < 256 + sizeof(czk::TokMeta) * n) { set_error("inflate count workspace too small"); return CZ_E_MEM; }
+    czk::TwoPhaseParams Q;
+    memset(&Q, 0, sizeof Q);
+    Q.base.in = d_in; Q.base.in_off = d_in_off; Q.base.out = nullptr; Q.base.out_off = d_out_off; Q.base.in_consumed = d_in_consumed;
+    Q.base.counter = (unsigned long long *)d_ws; Q.base.crc = ctx->d_crc; Q.base.n = (uint32_t)n; Q.base.ids = nullptr;
+    Q.base.window_bits = window_bits; Q.base.segment_mode = segment_mode; Q.base.check_kind = 0;
+    Q.meta = (czk::TokMeta *)((uint8_t *)d_ws + 256);
+    Q.count_only = 1;
+    if (d_meta_ret) *d_meta_ret = Q.meta;
+    if (!CZ_CUDA(cudaMemsetAsync(d_ws, 0, 256, st))) return CZ_E_MEM;
+    constexpr int WA = 14;
+    auto ka = czk::inflate_tok_kernel<WA>;
+    const size_t smem = czk::inflate_tok_smem_bytes<WA>();
+    static bool configured[64] = {};
+    static int per_sm[64];
+    const int d = ctx->dev & 63;
+    if (!configured[d]) {
+        if (!CZ_CUDA(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return CZ_E_MEM;
+        if (!CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[d], ka, WA * 32, smem))) return CZ_E_MEM;
+        if (per_sm[d] < 1) { set_error("inflate_tok_kernel does not fit on an SM"); return CZ_E_MEM; }
+        configured[d] = true;
+    }
+    // spread the units over as many SMs as possible: one warp's worth of lanes per CTA slot is enough for a few thousand pieces
+    uint64_t ga = (n + 31) / 32, gmax = (uint64_t)ctx->sm_count * per_sm[d];
+    if (ga > gmax) ga = gmax;
+    ka<<<(unsigned)ga, WA * 32, smem, st>>>(Q);
     return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
 }
 

@@ -710,8 +710,10 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
             const bool fin = st == SS_TRAILER || st == SS_FINISH;
             bool want_adler = false, want_crc = false;
             if (lane < D && st != SS_EXIT && st != SS_IDLE) {
-                want_adler = P.segment_mode ? (P.check_kind & 1) : wrap == 1;
-                want_crc = P.segment_mode ? (P.check_kind & 2) : wrap == 2;
+                // raw units asked for checks (pieces of a longer stream): both, like segment mode
+                const bool by_kind = P.segment_mode || (P.checks && wrap == 0);
+                want_adler = by_kind ? (P.check_kind & 1) : wrap == 1;
+                want_crc = by_kind ? (P.check_kind & 2) : wrap == 2;
             }
             uint64_t pending = out_pos - ck_pos;
             bool go = (want_adler || want_crc) && (fin ? pending > 0 : pending >= 4096);

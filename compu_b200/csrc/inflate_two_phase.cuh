@@ -44,6 +44,7 @@ struct TwoPhaseParams {
     uint32_t *tok;               // token area: unit u starts at word tok_word_off(out_off[u] - out_off[0], u)
     TokMeta *meta;               // n
     unsigned long long *counter_b;  // phase B work counter, zero before launch
+    int32_t count_only;          // phase A only: no tokens are written, TokMeta.out_len / status / in_consumed are the result
 };
 
 __host__ __device__ inline uint64_t tok_word_off(uint64_t out_off, uint64_t unit) { return out_off + 8 * unit; }
@@ -80,7 +81,9 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
     int result = 0, wrap = 0;
     uint32_t bfinal = 0, nlit_sym = 0, ndist_sym = 0, stored_len = 0, expect = 0;
 
-#define CZK_FLUSH_LIT() do { if (nlit) { *tp++ = CZK_TOK_LIT | (nlit << 24) | lit; lit = 0; nlit = 0; } } while (0)
+    const bool emit = !Q.count_only;
+#define CZK_PUT(x) do { if (emit) *tp++ = (x); } while (0)
+#define CZK_FLUSH_LIT() do { if (nlit) { CZK_PUT(CZK_TOK_LIT | (nlit << 24) | lit); lit = 0; nlit = 0; } } while (0)
 
     for (;;) {
         // ---- (1) fetch work
@@ -92,7 +95,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
                 uint64_t i0 = P.in_off[unit], i1 = P.in_off[unit + 1], o0 = P.out_off[unit], o1 = P.out_off[unit + 1];
                 in_base = P.in + i0; in_len = i1 - i0;
                 cap = o1 - o0; pos = 0;
-                tp0 = tp = Q.tok + tok_word_off(o0 - P.out_off[0], unit);
+                tp0 = tp = emit ? Q.tok + tok_word_off(o0 - P.out_off[0], unit) : nullptr;
                 lit = 0; nlit = 0; bfinal = 0; result = 0; expect = 0;
                 br.init(in_base, in_len);
                 st = SS_HEADER;
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
                     if (pos >= cap) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
                     pos++;
                     lit |= sym << (8 * nlit);
-                    if (++nlit == 3) { *tp++ = CZK_TOK_LIT | (3u << 24) | lit; lit = 0; nlit = 0; }
+                    if (++nlit == 3) { CZK_PUT(CZK_TOK_LIT | (3u << 24) | lit); lit = 0; nlit = 0; }
                     continue;
                 }
                 if (sym == 256) {  // end of block
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
                 uint32_t n = len;
                 if (pos + n > cap) n = (uint32_t)(cap - pos);
                 CZK_FLUSH_LIT();
-                *tp++ = n | (dist << 9);
+                CZK_PUT(n | (dist << 9));
                 pos += n;
                 if (n < len) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
             }
@@ -236,13 +239,13 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
             if (pos + n > cap) { n = (uint32_t)(cap - pos); err = ST_NEED_OUTPUT; }
             if (n > 8) {
                 CZK_FLUSH_LIT();
-                *tp++ = CZK_TOK_STORED | n;
-                *tp++ = CZK_TOK_STORED | (uint32_t)(ipos & 0x3fffffffu);
-                *tp++ = CZK_TOK_STORED | (uint32_t)(ipos >> 30);
+                CZK_PUT(CZK_TOK_STORED | n);
+                CZK_PUT(CZK_TOK_STORED | (uint32_t)(ipos & 0x3fffffffu));
+                CZK_PUT(CZK_TOK_STORED | (uint32_t)(ipos >> 30));
             } else {
                 for (uint32_t k = 0; k < n; k++) {
                     lit |= (uint32_t)in_base[ipos + k] << (8 * nlit);
-                    if (++nlit == 3) { *tp++ = CZK_TOK_LIT | (3u << 24) | lit; lit = 0; nlit = 0; }
+                    if (++nlit == 3) { CZK_PUT(CZK_TOK_LIT | (3u << 24) | lit); lit = 0; nlit = 0; }
                 }
             }
             pos += n;
@@ -291,6 +294,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
         }
     }
 #undef CZK_FLUSH_LIT
+#undef CZK_PUT
 }
 
 template <int WARPS>
@@ -320,8 +324,9 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lz_kernel(TwoPhaseParams Q
         const uint8_t *ib = P.in + P.in_off[unit];
         const uint32_t *tok = Q.tok + tok_word_off(o0 - P.out_off[0], unit);
         const uint32_t ntok = m.ntok;
-        const bool want_adler = P.segment_mode ? (P.check_kind & 1) : m.wrap == 1;
-        const bool want_crc = P.segment_mode ? (P.check_kind & 2) : m.wrap == 2;
+        const bool by_kind = P.segment_mode || (P.checks && m.wrap == 0);  // raw units asked for checks: pieces of a longer stream
+        const bool want_adler = by_kind ? (P.check_kind & 1) : m.wrap == 1;
+        const bool want_crc = by_kind ? (P.check_kind & 2) : m.wrap == 2;
         uint64_t opos = 0, ck_pos = 0;
         uint32_t adler = 1, crc = 0;
         uint32_t ti = 0;

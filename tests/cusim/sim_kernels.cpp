@@ -39,7 +39,7 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
             std::vector<TokMeta> meta(n);
             unsigned long long counter_b = 0;
             TwoPhaseParams Q;
-            Q.base = P; Q.tok = tok.data(); Q.meta = meta.data(); Q.counter_b = &counter_b;
+            Q.base = P; Q.tok = tok.data(); Q.meta = meta.data(); Q.counter_b = &counter_b; Q.count_only = 0;
             cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2>, Q);
             if (D == -3) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 0>, Q);
             else if (seed % 3 == 0) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 4>, Q);
