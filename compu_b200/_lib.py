@@ -49,6 +49,7 @@ SIGNATURES = {
     "cz_deflate_workspace_bytes": (u64, [sz, u64]),
     "cz_deflate_segments_device": (ci, [vp, sz, vp, vp, u64, vp, vp, vp, vp, vp, ci, ci, vp, u64]),
     "cz_partition_by_bytes": (ci, [sz, vp, ci, vp]),
+    "cz_split_stats": (None, [vp, vp]),
     "cz_profile_enable": (None, [ci]),
     "cz_profile_read": (ci, [vp, vp]),
     "cz_adler32_combine": (u32, [u32, u32, u64]),

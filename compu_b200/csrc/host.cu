@@ -213,12 +213,13 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
     for (size_t i = 0; i <= n; i++) { offs[i] = in_off[u0 + i] - ib; offs[n + 1 + i] = out_off[u0 + i] - ob; }
     uint8_t *dm = w.meta.as<uint8_t>();
     if (!CZ_CUDA(cudaMemcpyAsync(dm, offs.data(), 16 * (n + 1), cudaMemcpyHostToDevice, w.streams[0]))) return CZ_E_MEM;
-    if (any_big && !CZ_CUDA(cudaMemcpyAsync(dm + m_ids, ids.data(), 4 * n, cudaMemcpyHostToDevice, w.streams[0]))) return CZ_E_MEM;
+    if (any_big && !ids.empty() && !CZ_CUDA(cudaMemcpyAsync(dm + m_ids, ids.data(), 4 * ids.size(), cudaMemcpyHostToDevice, w.streams[0]))) return CZ_E_MEM;
     if (!CZ_CUDA(cudaStreamSynchronize(w.streams[0]))) return CZ_E_MEM;  // `offs`/`ids` are stack-lifetime pageable buffers
     for (size_t k = 0; k < nsub; k++) {
         cudaStream_t st = w.streams[k % CZ_INFLATE_STREAMS];
         const size_t a = cut[k], b = cut[k + 1], nk = b - a;
         const uint64_t ia = offs[a], ibk = offs[b], oa = offs[n + 1 + a], obk = offs[n + 1 + b];
+        if (any_big && !n_small[k] && !n_big[k]) continue;  // every unit of this sub-batch was decoded by the speculative split
         if (ibk > ia && !CZ_CUDA(cudaMemcpyAsync(w.in.as<uint8_t>() + ia, in + ib + ia, ibk - ia, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
         const uint32_t *d_ids = any_big ? (const uint32_t *)(dm + m_ids) + ids_at[k] : nullptr;
         uint8_t *wsk = w.ws.as<uint8_t>() + ws_off[k];
@@ -233,7 +234,20 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
                                    d_ids ? d_ids + (big ? n_small[k] : 0) : nullptr, big ? n_big[k] : n_small[k], big);
             if (r) return r;
         }
-        if (obk > oa && !CZ_CUDA(cudaMemcpyAsync(out + ob + oa, w.out.as<uint8_t>() + oa, obk - oa, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+        if (!skip) {
+            if (obk > oa && !CZ_CUDA(cudaMemcpyAsync(out + ob + oa, w.out.as<uint8_t>() + oa, obk - oa, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+        } else {
+            // units already decoded in place by the speculative split must not be overwritten: copy the runs between them
+            size_t i = a;
+            while (i < b) {
+                while (i < b && skip[u0 + i]) i++;
+                size_t e = i;
+                while (e < b && !skip[u0 + e]) e++;
+                const uint64_t ra = offs[n + 1 + i], rb = offs[n + 1 + e];
+                if (rb > ra && !CZ_CUDA(cudaMemcpyAsync(out + ob + ra, w.out.as<uint8_t>() + ra, rb - ra, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+                i = e;
+            }
+        }
         if (!CZ_CUDA(cudaMemcpyAsync(w.res_lens + a, dm + m_lens + 8 * a, 8 * nk, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
         if (!CZ_CUDA(cudaMemcpyAsync(w.res_stat + a, dm + m_stat + 4 * a, 4 * nk, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
         if (in_consumed && !CZ_CUDA(cudaMemcpyAsync(w.res_cons + a, dm + m_cons + 8 * a, 8 * nk, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
@@ -262,7 +276,7 @@ static void split_by_bytes(size_t n, const uint64_t *off, int parts, std::vector
 // cut after every `00 00 ff ff` marker and the pieces decoded independently. Nothing in the stream says which markers are
 // real, so every step is verified instead of assumed:
 //   1. candidate cuts = occurrences of 00 00 ff ff (thinned to pieces of >= 256 KiB);
-//   2. COUNT pass (phase A of the two-phase kernel, no output): piece j decoded as a history-free raw fragment must end
+//   2. COUNT pass (the warp-per-stream kernel in counting mode, no output): piece j decoded as a history-free raw fragment must end
 //      exactly at the next cut at a block boundary (=> the cut IS a block boundary) and must never reference bytes before
 //      its own start (=> no history crosses the cut). A failing piece is merged with its neighbours and recounted;
 //   3. with every piece verified and sized, the pieces are decoded in parallel into their final places with per-piece
@@ -279,13 +293,6 @@ struct CountWork {
     }
 };
 
-struct CountMeta {  // == czk::TokMeta (inflate_two_phase.cuh)
-    uint32_t ntok;
-    int32_t status;
-    uint64_t out_len;
-    uint32_t expect, wrap;
-};
-
 // sizes / statuses / consumed bytes of the pieces [in_off[j], in_off[j+1]) of `in`; dev_in_valid: the device copy is current
 static int inflate_count_host(CountWork &w, int dev, const uint8_t *in, uint64_t in_bytes, bool &dev_in_valid, size_t n,
                               const uint64_t *in_off, int window_bits, int segment_mode, uint64_t *out_lens, int32_t *statuses,
@@ -293,9 +300,9 @@ static int inflate_count_host(CountWork &w, int dev, const uint8_t *in, uint64_t
     DeviceCtx *ctx = device_ctx(dev);
     if (!ctx) return CZ_E_NO_DEVICE;
     if (!CZ_CUDA(cudaSetDevice(dev)) || !w.init(dev)) return CZ_E_MEM;
-    // meta: in_off[n+1] caps[n+1] consumed[n] | ws: counter 256 + CountMeta[n]
-    const size_t m_cap = 8 * (n + 1), m_cons = m_cap + 8 * (n + 1), m_ws = align_up(m_cons + 8 * n, 256),
-                 m_total = m_ws + 256 + sizeof(CountMeta) * n;
+    // meta: in_off[n+1] caps[n+1] lens[n] consumed[n] statuses[n] | counter 256
+    const size_t m_cap = 8 * (n + 1), m_len = m_cap + 8 * (n + 1), m_cons = m_len + 8 * n, m_stat = m_cons + 8 * n,
+                 m_ws = align_up(m_stat + 4 * n, 256), m_total = m_ws + 256;
     if (!w.in.reserve(in_bytes + 16) || !w.meta.reserve(m_total)) return CZ_E_MEM;
     std::vector<uint64_t> h(2 * (n + 1));
     for (size_t i = 0; i <= n; i++) { h[i] = in_off[i]; h[n + 1 + i] = (uint64_t)i << 40; }  // "unlimited" output slots
@@ -304,15 +311,14 @@ static int inflate_count_host(CountWork &w, int dev, const uint8_t *in, uint64_t
     if (!dev_in_valid && in_bytes && !CZ_CUDA(cudaMemcpyAsync(w.in.p, in, in_bytes, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
     dev_in_valid = true;
     if (!CZ_CUDA(cudaMemcpyAsync(dm, h.data(), 16 * (n + 1), cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
-    void *d_meta = nullptr;
     int rc = launch_inflate_count(st, ctx, n, w.in.as<uint8_t>(), (const uint64_t *)dm, (const uint64_t *)(dm + m_cap),
-                                  (uint64_t *)(dm + m_cons), window_bits, segment_mode, dm + m_ws, 256 + sizeof(CountMeta) * n, &d_meta);
+                                  (uint64_t *)(dm + m_len), (int32_t *)(dm + m_stat), (uint64_t *)(dm + m_cons), window_bits,
+                                  segment_mode, dm + m_ws, 256);
     if (rc) return rc;
-    std::vector<CountMeta> hm(n);
-    if (!CZ_CUDA(cudaMemcpyAsync(hm.data(), d_meta, sizeof(CountMeta) * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+    if (!CZ_CUDA(cudaMemcpyAsync(out_lens, dm + m_len, 8 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
     if (!CZ_CUDA(cudaMemcpyAsync(consumed, dm + m_cons, 8 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+    if (!CZ_CUDA(cudaMemcpyAsync(statuses, dm + m_stat, 4 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
     if (!CZ_CUDA(cudaStreamSynchronize(st))) return CZ_E_MEM;
-    for (size_t i = 0; i < n; i++) { out_lens[i] = hm[i].out_len; statuses[i] = hm[i].status; }
     return 0;
 }
 
@@ -334,6 +340,8 @@ static long host_header_len(const uint8_t *p, uint64_t n, int window_bits, int &
     if (flg & 2) return -1;
     return o <= n ? (long)o : -1;
 }
+
+static uint64_t g_split_ok = 0, g_split_tried = 0;  // statistics (cz_split_stats)
 
 static uint64_t huge_unit_bytes() {
     static uint64_t v = 0;
@@ -470,8 +478,10 @@ int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint
         for (size_t i = 0; i < n; i++) {
             if (in_off[i + 1] - in_off[i] < huge_unit_bytes()) continue;
             Done d{i, 0, 0, 0};
+            g_split_tried++;
             if (inflate_split_speculative(in + in_off[i], in_off[i + 1] - in_off[i], out + out_off[i], out_off[i + 1] - out_off[i],
                                           window_bits, devices_mask, &d.len, &d.st, &d.cons)) {
+                g_split_ok++;
                 if (skip.empty()) skip.assign(n, 0);
                 skip[i] = 1;
                 done.push_back(d);
@@ -543,6 +553,11 @@ extern "C" const char *cz_describe_error(int32_t code) {
         case -6: return "incompatible version";
         default: return "";
     }
+}
+
+extern "C" void cz_split_stats(uint64_t *tried, uint64_t *split) {
+    if (tried) *tried = g_split_tried;
+    if (split) *split = g_split_ok;
 }
 
 extern "C" int cz_partition_by_bytes(size_t n, const uint64_t *offsets, int parts, uint64_t *cuts) {

@@ -57,8 +57,8 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
                    uint64_t total_out_bytes, const uint32_t *d_ids, size_t n_ids, int big);
 uint64_t inflate_workspace_bytes(size_t n, uint64_t total_out_bytes);
 int launch_inflate_count(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
-                         const uint64_t *d_out_off, uint64_t *d_in_consumed, int window_bits, int segment_mode, void *d_ws,
-                         uint64_t ws_bytes, void **d_meta_ret);
+                         const uint64_t *d_out_off, uint64_t *d_out_lens, int32_t *d_statuses, uint64_t *d_in_consumed,
+                         int window_bits, int segment_mode, void *d_ws, uint64_t ws_bytes);
 
 // batched inflate over host memory (host.cu); segment_mode / checks as in cz_inflate_segments_device
 int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint8_t *out, const uint64_t *out_off,

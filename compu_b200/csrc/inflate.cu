@@ -143,39 +143,22 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
 }
 
 
-// Phase A alone in counting mode: output size, status and consumed bytes of every unit, nothing written but TokMeta.
-// Workspace: [counter 256 B][TokMeta n]. The caller reads the TokMeta array (device pointer returned) after the stream.
+// Counting mode: output size, status and consumed bytes of every unit, no output bytes (the speculative split's verify pass).
+// Runs the warp-per-stream kernel (a lone decoder lane per unit is ~6x faster per stream than the lane-per-stream kernels,
+// and pieces are few and large). Workspace: 256 B.
 int launch_inflate_count(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
-                         const uint64_t *d_out_off, uint64_t *d_in_consumed, int window_bits, int segment_mode, void *d_ws,
-                         uint64_t ws_bytes, void **d_meta_ret) {
+                         const uint64_t *d_out_off, uint64_t *d_out_lens, int32_t *d_statuses, uint64_t *d_in_consumed,
+                         int window_bits, int segment_mode, void *d_ws, uint64_t ws_bytes) {
     if (n == 0) return 0;
-    if (n > 0xfffffff0u || !d_ws || ws_bytes < 256 + sizeof(czk::TokMeta) * n) { set_error("inflate count workspace too small"); return CZ_E_MEM; }
-    czk::TwoPhaseParams Q;
-    memset(&Q, 0, sizeof Q);
-    Q.base.in = d_in; Q.base.in_off = d_in_off; Q.base.out = nullptr; Q.base.out_off = d_out_off; Q.base.in_consumed = d_in_consumed;
-    Q.base.counter = (unsigned long long *)d_ws; Q.base.crc = ctx->d_crc; Q.base.n = (uint32_t)n; Q.base.ids = nullptr;
-    Q.base.window_bits = window_bits; Q.base.segment_mode = segment_mode; Q.base.check_kind = 0;
-    Q.meta = (czk::TokMeta *)((uint8_t *)d_ws + 256);
-    Q.count_only = 1;
-    if (d_meta_ret) *d_meta_ret = Q.meta;
+    if (n > 0xfffffff0u || !d_ws || ws_bytes < 256) { set_error("inflate count workspace too small"); return CZ_E_MEM; }
+    czk::InflateParams P;
+    memset(&P, 0, sizeof P);
+    P.in = d_in; P.in_off = d_in_off; P.out = nullptr; P.out_off = d_out_off; P.out_lens = d_out_lens; P.statuses = d_statuses;
+    P.in_consumed = d_in_consumed; P.checks = nullptr; P.counter = (unsigned long long *)d_ws; P.crc = ctx->d_crc;
+    P.n = (uint32_t)n; P.ids = nullptr; P.window_bits = window_bits; P.segment_mode = segment_mode; P.check_kind = 0;
+    P.count_only = 1;
     if (!CZ_CUDA(cudaMemsetAsync(d_ws, 0, 256, st))) return CZ_E_MEM;
-    constexpr int WA = 14;
-    auto ka = czk::inflate_tok_kernel<WA>;
-    const size_t smem = czk::inflate_tok_smem_bytes<WA>();
-    static bool configured[64] = {};
-    static int per_sm[64];
-    const int d = ctx->dev & 63;
-    if (!configured[d]) {
-        if (!CZ_CUDA(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return CZ_E_MEM;
-        if (!CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm[d], ka, WA * 32, smem))) return CZ_E_MEM;
-        if (per_sm[d] < 1) { set_error("inflate_tok_kernel does not fit on an SM"); return CZ_E_MEM; }
-        configured[d] = true;
-    }
-    // spread the units over as many SMs as possible: one warp's worth of lanes per CTA slot is enough for a few thousand pieces
-    uint64_t ga = (n + 31) / 32, gmax = (uint64_t)ctx->sm_count * per_sm[d];
-    if (ga > gmax) ga = gmax;
-    ka<<<(unsigned)ga, WA * 32, smem, st>>>(Q);
-    return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
+    return launch_cfg<1, 8>(st, ctx, P);
 }
 
 static InflateCfg g_cfg = {0, 0};
@@ -207,7 +190,7 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
     P.in = d_in; P.in_off = d_in_off; P.out = d_out; P.out_off = d_out_off; P.out_lens = d_out_lens; P.statuses = d_statuses;
     P.in_consumed = d_in_consumed; P.checks = d_checks; P.counter = (unsigned long long *)d_ws; P.crc = ctx->d_crc;
     P.n = (uint32_t)(d_ids ? n_ids : n); P.ids = d_ids;
-    P.window_bits = window_bits; P.segment_mode = segment_mode; P.check_kind = check_kind;
+    P.window_bits = window_bits; P.segment_mode = segment_mode; P.check_kind = check_kind; P.count_only = 0;
     if (!CZ_CUDA(cudaMemsetAsync(d_ws, 0, 256, st))) return CZ_E_MEM;
     InflateCfg c = pick_cfg();
     // big units (one stream is megabytes): one WARP per stream, a single decoder lane feeding warp-cooperative LZ77 rounds —

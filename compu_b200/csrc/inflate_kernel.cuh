@@ -48,6 +48,7 @@ struct InflateParams {
     int32_t window_bits;      // -15 raw, 15 zlib, 31 gzip, 47 auto
     int32_t segment_mode;     // 1: raw full-flush segments: end of input at a block boundary is success
     int32_t check_kind;       // segment_mode only: bit0 adler, bit1 crc into `checks`
+    int32_t count_only;       // inflate_kernel only: produce no output bytes, just sizes / statuses / consumed (out may be null)
 };
 
 // litlen table entry (u16): bits 0-3 code length, bits 4-15 payload
@@ -632,6 +633,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 int rel = -(int)(a0 & 31);                             // batch-relative index of this round's lane 0
                 uint32_t cnt_before = 0;
                 uint8_t *obp = ob + opos;
+                if (P.count_only) rel = (int)total;  // sizes only: the tokens' lengths are all that is needed
                 for (; rel < (int)total; rel += 32) {
                     // which tokens start inside this round?
                     uint32_t bit = (lane < nt && (int)pos >= rel && (int)pos < rel + 32) ? 1u << ((int)pos - rel) : 0u;
@@ -692,7 +694,8 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 uint32_t n = len;
                 if (ipos + n > ilen) { n = (uint32_t)(ilen - ipos); err = ST_NEED_INPUT; }
                 if (opos + n > ocap) { n = (uint32_t)(ocap - opos); err = ST_NEED_OUTPUT; }
-                for (uint32_t k = lane; k < n; k += 32) ob[opos + k] = ib[ipos + k];
+                if (!P.count_only)
+                    for (uint32_t k = lane; k < n; k += 32) ob[opos + k] = ib[ipos + k];
                 __syncwarp();
                 if ((int)lane == s) {
                     out_pos = opos + n;
@@ -716,7 +719,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 want_crc = by_kind ? (P.check_kind & 2) : wrap == 2;
             }
             uint64_t pending = out_pos - ck_pos;
-            bool go = (want_adler || want_crc) && (fin ? pending > 0 : pending >= 4096);
+            bool go = !P.count_only && (want_adler || want_crc) && (fin ? pending > 0 : pending >= 4096);
             uint32_t m = __ballot_sync(CZK_FULL, go);
             while (m) {
                 int s = __ffs(m) - 1;

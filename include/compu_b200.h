@@ -176,6 +176,11 @@ int cz_deflate_segments_device(void *cuda_stream, size_t n, const uint8_t *d_in,
 uint32_t cz_adler32_combine(uint32_t adler1, uint32_t adler2, uint64_t len2);
 uint32_t cz_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
 
+/* Long single streams (>= 2 MiB compressed) given to the inflate entry points are split speculatively at full-flush markers
+   and decoded in parallel when every piece verifies (compu_b200/csrc/host.cu); otherwise they take the serial path. Counters
+   since load: units the split was tried on / units decoded by it. */
+void cz_split_stats(uint64_t *tried, uint64_t *split);
+
 /* The multi-GPU partitioner used by the batched entry points: cuts n packed units (offsets[n+1]) into `parts`
    contiguous ranges balanced by bytes, no collective. cuts[parts+1] receives unit indices, cuts[0] = 0, cuts[parts] = n.
    Pure host arithmetic (no device needed), exported so that callers sharding over processes use the same cuts. */

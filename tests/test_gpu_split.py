@@ -25,6 +25,13 @@ def _text(alice, n, seed=1):
     return b"".join(parts)[:n]
 
 
+def _split_stats():
+    import ctypes
+    a, b = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    _lib.lib().cz_split_stats(ctypes.byref(a), ctypes.byref(b))
+    return a.value, b.value
+
+
 def _check_vs_oracle(streams, caps, wbits):
     outs, st, lens, cons = batch.inflate_batch(streams, caps, wbits)
     ref_outs, ref_st, _ = oracle_inflate(streams, caps, wbits)
@@ -39,7 +46,10 @@ def _check_vs_oracle(streams, caps, wbits):
 def test_own_long_stream_decodes_through_ordinary_api(alice, wbits):
     data = _text(alice, 24_000_000, 3)
     stream, idx = batch.deflate_segmented(data, level=6, window_bits=wbits, segment_bytes=1 << 20)
+    t0, s0 = _split_stats()
     outs, st, cons = _check_vs_oracle([stream, stream + b"trailing garbage"], [len(data), len(data) + 100], wbits)
+    t1, s1 = _split_stats()
+    assert (t1 - t0, s1 - s0) == (2, 2), "both long streams must have been decoded by the parallel split"
     assert list(st) == [2, 2] and outs[0] == data and outs[1] == data
     assert list(cons) == [len(stream), len(stream)]
 
@@ -54,7 +64,11 @@ def test_zlib_full_flush_and_sync_flush_streams(alice):
             parts.append(c.flush(flush))
         parts.append(c.flush())
         s = b"".join(parts)
+        t0, s0 = _split_stats()
         outs, st, cons = _check_vs_oracle([s], [len(data)], 31)
+        t1, s1 = _split_stats()
+        # full-flush points split; sync-flush points are tried, fail verification (history crosses them) and fall back
+        assert (t1 - t0, s1 - s0) == ((1, 1) if flush == zlib.Z_FULL_FLUSH else (1, 0))
         assert st[0] == 2 and outs[0] == data and cons[0] == len(s)
 
 
