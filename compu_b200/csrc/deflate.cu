@@ -706,12 +706,13 @@ extern "C" void *cz_encoder_reset(void *state) {
 
 extern "C" void cz_encoder_free(void *state) { delete (EncoderState *)state; }
 
-// compress everything staged; append to the pending queue
-static int encoder_flush_staged(EncoderState *s, bool finish) {
+// Compress the first `nbytes` staged bytes (segments + flush markers) and append them to the pending queue; with nothing to
+// compress, `empty_marker` appends the bare marker (what zlib emits for an empty sync flush); `finish` closes the stream.
+static int encoder_emit(EncoderState *s, size_t nbytes, bool empty_marker, bool finish) {
     const uint32_t hb = container_hdr_bytes(s->window_bits), tb = container_trl_bytes(s->window_bits);
     const uint64_t S = clamp_segment(0);
-    const uint64_t nseg = s->in_len ? (s->in_len + S - 1) / S : 1;
-    const uint64_t need = hb + segment_bound(s->in_len) + 64 * nseg + 2 + tb + 16;
+    const uint64_t nseg = nbytes ? (nbytes + S - 1) / S : 1;
+    const uint64_t need = hb + segment_bound(nbytes) + 64 * nseg + 2 + tb + 16;
     // compact the queue first
     if (s->pend_pos) {
         memmove(s->pend.p, s->pend.as<uint8_t>() + s->pend_pos, s->pend_len - s->pend_pos);
@@ -722,27 +723,25 @@ static int encoder_flush_staged(EncoderState *s, bool finish) {
     uint8_t *o = s->pend.as<uint8_t>() + s->pend_len;
     size_t k = 0;
     if (!s->header_done) { k += write_header(o, s->window_bits, s->level); s->header_done = true; }
-    if (s->in_len || !finish) {
+    if (nbytes) {
         EngineJob J;
-        uint64_t off[2] = {0, s->in_len};
+        uint64_t off[2] = {0, nbytes};
         J.in = s->in.as<uint8_t>(); J.unit_off = off; J.n = 1; J.seg_bytes = S; J.level = s->level; J.strategy = s->strategy;
         J.check_kind = s->window_bits == 15 ? 1 : s->window_bits > 15 ? 2 : 0;
         J.dst.assign(1, o + k); J.dst_cap.assign(1, need - k);
-        if (s->in_len == 0) {
-            // empty flush: just the marker (zlib emits the same empty stored block)
-            const uint8_t m[5] = {0x00, 0x00, 0x00, 0xff, 0xff};
-            memcpy(o + k, m, 5);
-            k += 5;
-        } else {
-            int rc = deflate_engine(J, 1);
-            if (rc) return rc;
-            if (J.res[0].status != CZ_ENCODE_FINISHED) { set_error("internal: staged output bound too small"); return CZ_E_MEM; }
-            k += J.res[0].payload_len;
-            s->adler = czk::adler32_combine_u(s->adler, J.res[0].adler, s->in_len);
-            s->crc = czk::crc32_combine_u(s->crc, J.res[0].crc, s->in_len);
-        }
-        s->total_in += s->in_len;
-        s->in_len = 0;
+        int rc = deflate_engine(J, 1);
+        if (rc) return rc;
+        if (J.res[0].status != CZ_ENCODE_FINISHED) { set_error("internal: staged output bound too small"); return CZ_E_MEM; }
+        k += J.res[0].payload_len;
+        s->adler = czk::adler32_combine_u(s->adler, J.res[0].adler, nbytes);
+        s->crc = czk::crc32_combine_u(s->crc, J.res[0].crc, nbytes);
+        s->total_in += nbytes;
+        if (nbytes < s->in_len) memmove(s->in.p, s->in.as<uint8_t>() + nbytes, s->in_len - nbytes);
+        s->in_len -= nbytes;
+    } else if (empty_marker) {
+        const uint8_t m[5] = {0x00, 0x00, 0x00, 0xff, 0xff};
+        memcpy(o + k, m, 5);
+        k += 5;
     }
     if (finish) {
         o[k++] = 0x03; o[k++] = 0x00;
@@ -752,6 +751,12 @@ static int encoder_flush_staged(EncoderState *s, bool finish) {
     s->pend_len += k;
     return 0;
 }
+
+// Staged input is compressed in slices of this many bytes as soon as they are complete, so a long Process() sequence
+// neither holds the whole input in pinned memory nor leaves all the work to Finish. The slice is a multiple of the segment
+// size and slices start at multiples of it, so the segments — and therefore the compressed bytes — are exactly those of a
+// one-shot call (tests/encoder.rs:56-57, 65-66: output must not depend on the caller's chunking).
+static const size_t kEncoderSlice = 64u << 20;
 
 extern "C" cz_result cz_encode(void *state, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len, int op) {
     EncoderState *s = (EncoderState *)state;
@@ -767,8 +772,11 @@ extern "C" cz_result cz_encode(void *state, const uint8_t *in, size_t in_len, ui
         s->in_len += in_len;
     }
     r.input_remain = 0;  // like zlib, all input is taken into the window/staging (tests/encoder.rs:17-18)
+    while (!s->finished && s->in_len >= kEncoderSlice + (op == CZ_OP_PROCESS ? 0 : 1)) {
+        if (encoder_emit(s, kEncoderSlice, false, false)) { s->error = true; return r; }
+    }
     if (!s->finished && ((op == CZ_OP_FLUSH && (s->in_len || s->pend_pos == s->pend_len)) || op == CZ_OP_FINISH)) {
-        int rc = encoder_flush_staged(s, op == CZ_OP_FINISH);
+        int rc = encoder_emit(s, s->in_len, op == CZ_OP_FLUSH, op == CZ_OP_FINISH);
         if (rc) { s->error = true; return r; }
     }
     size_t avail = s->pend_len - s->pend_pos;

@@ -316,3 +316,25 @@ def test_full_size_deflate_4gib_single_stream():
     assert got.value == n
     for o in range(0, n, 1 << 28):
         assert np.array_equal(back[o:o + (1 << 28)], src[o:o + (1 << 28)])
+
+
+def test_streaming_encoder_slices_match_one_shot(alice):
+    """A long Process() sequence is compressed slice by slice (64 MiB) as the input arrives; the bytes must be exactly those of
+    a single Finish call with the whole input (tests/encoder.rs:56-57: output independent of the caller's chunking)."""
+    from compu_b200 import Vec
+    data = (alice * 1000)[:150_000_000]
+    one = cuda_encoder(enc.ZlibMode.Zlib, 6)
+    v1 = Vec()
+    r = one.encode_vec_full(data, v1, enc.EncodeOp.Finish)
+    assert r.status == enc.EncodeStatus.Finished
+    chunked = cuda_encoder(enc.ZlibMode.Zlib, 6)
+    v2 = Vec()
+    step = 7_000_003
+    for o in range(0, len(data), step):
+        v2.reserve(1 << 20)
+        r = chunked.encode_vec(data[o:o + step], v2, enc.EncodeOp.Process)
+        assert r.status == enc.EncodeStatus.Continue and r.input_remain == 0
+    r = chunked.encode_vec_full(b"", v2, enc.EncodeOp.Finish)
+    assert r.status == enc.EncodeStatus.Finished
+    assert v1.as_bytes() == v2.as_bytes()
+    assert zlib.decompress(v1.as_bytes()) == data
