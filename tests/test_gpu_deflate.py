@@ -320,21 +320,30 @@ def test_full_size_deflate_4gib_single_stream():
 
 def test_streaming_encoder_slices_match_one_shot(alice):
     """A long Process() sequence is compressed slice by slice (64 MiB) as the input arrives; the bytes must be exactly those of
-    a single Finish call with the whole input (tests/encoder.rs:56-57: output independent of the caller's chunking)."""
-    from compu_b200 import Vec
-    data = (alice * 1000)[:150_000_000]
-    one = cuda_encoder(enc.ZlibMode.Zlib, 6)
-    v1 = Vec()
-    r = one.encode_vec_full(data, v1, enc.EncodeOp.Finish)
-    assert r.status == enc.EncodeStatus.Finished
-    chunked = cuda_encoder(enc.ZlibMode.Zlib, 6)
-    v2 = Vec()
+    a single Finish call with the whole input (tests/encoder.rs:56-57: output independent of the caller's chunking).
+    Driven through the raw C ABI with preallocated buffers (the Vec mirror reallocates per call, which is quadratic here)."""
+    L = _lib.lib()
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    data = np.frombuffer((alice * 1000)[:150_000_000], dtype=np.uint8)
+    cap = int(L.cz_deflate_bound(len(data), 15, 0))
+
+    def run(chunks):
+        st = L.cz_encoder_new(6, 15, 8, 0)
+        assert st, _lib.last_error()
+        out = np.empty(cap, dtype=np.uint8)
+        pos = 0
+        for c in chunks:
+            r = L.cz_encode(st, p(c) if len(c) else p(out), len(c), ctypes.c_void_p(out.ctypes.data + pos), cap - pos, 0)
+            assert r.status == 0 and r.input_remain == 0
+            pos += cap - pos - r.output_remain
+        r = L.cz_encode(st, p(out), 0, ctypes.c_void_p(out.ctypes.data + pos), cap - pos, 2)
+        assert r.status == 2
+        pos += cap - pos - r.output_remain
+        L.cz_encoder_free(st)
+        return out[:pos]
+
+    one = run([data])
     step = 7_000_003
-    for o in range(0, len(data), step):
-        v2.reserve(1 << 20)
-        r = chunked.encode_vec(data[o:o + step], v2, enc.EncodeOp.Process)
-        assert r.status == enc.EncodeStatus.Continue and r.input_remain == 0
-    r = chunked.encode_vec_full(b"", v2, enc.EncodeOp.Finish)
-    assert r.status == enc.EncodeStatus.Finished
-    assert v1.as_bytes() == v2.as_bytes()
-    assert zlib.decompress(v1.as_bytes()) == data
+    chunked = run([data[o:o + step] for o in range(0, len(data), step)])
+    assert len(one) == len(chunked) and np.array_equal(one, chunked)
+    assert zlib.decompress(one.tobytes()) == data.tobytes()
