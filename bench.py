@@ -77,6 +77,25 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def pin_to_gpu_numa_node(index):
+    """Runs this process on the CPUs NVML reports as local to GPU `index`, so that the pinned host buffers of the end-to-end
+    leg are allocated on the GPU's NUMA node (what a deployment does with numactl). Best effort; returns a short note."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w in range(words) for b in range(64) if (mask[w] >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return "pinned to %d CPUs local to GPU %d" % (len(cpus), index)
+        return "all CPUs are local to GPU %d" % index
+    except Exception as e:  # no NVML, no permission: run as is
+        return "unchanged (%s)" % type(e).__name__
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -442,6 +461,7 @@ def main():
     _lib.require_device()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = pin_to_gpu_numa_node(local_rank)  # before any pinned allocation: page-locked buffers land on the GPU's node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -591,7 +611,7 @@ def main():
             "config": {"workload": "cfg2: batched inflate of 65,536 independent 64 KiB zlib streams (Markov text, zlib 1.3 L6)",
                        "streams_per_gpu": n, "stream_bytes": STREAM_BYTES, "window_bits": 15, "ratio": U / C,
                        "l2": "inputs+outputs per step (%.2f GB) exceed the 126 MB L2; no flush needed" % ((U + C) / 1e9),
-                       "inflate_cfg": os.environ.get("CZ_INFLATE_CFG", "default"),
+                       "inflate_cfg": os.environ.get("CZ_INFLATE_CFG", "default"), "host_numa": numa,
                        "setup_s": {"synth_gpu": round(t_gen, 3), "zlib_compress_host": round(t_comp, 2)}},
             "e2e": e2e,
             "gpu_launches": 2 * args.steps,  # per step: inflate_tok_kernel + inflate_lz_kernel (plus a 256-byte memset node)

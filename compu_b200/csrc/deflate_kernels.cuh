@@ -169,31 +169,43 @@ __global__ void __launch_bounds__(32) deflate_chain_kernel(DeflateParams P) {
             for (uint32_t i = cn + lane; i < CZK_CHAIN_CHUNK + 8; i += 32) chunk[i] = 0;
             __syncwarp();
             const uint32_t cend = cb + CZK_CHAIN_CHUNK < n ? cb + CZK_CHAIN_CHUNK : n;
-            for (uint32_t base = cb; base < cend; base += 32) {
-                if (base && (base % CZK_CHAIN_SWEEP) == 0) {
+            // Four steps per iteration. What does not depend on the head table (bytes, hash, the grouping of equal hashes
+            // inside the step) is computed for all four first, so that those latencies overlap; only the table lookups
+            // and updates run one step after the other.
+            for (uint32_t base4 = cb; base4 < cend; base4 += 128) {
+                if (base4 && (base4 % CZK_CHAIN_SWEEP) == 0) {
                     for (uint32_t i = lane; i < (1u << CZK_HASH_BITS); i += 32)
-                        if (((base - (uint32_t)head[i]) & 0xffffu) >= CZK_WINDOW) head[i] = (uint16_t)((base - CZK_WINDOW) & 0xffffu);
+                        if (((base4 - (uint32_t)head[i]) & 0xffffu) >= CZK_WINDOW) head[i] = (uint16_t)((base4 - CZK_WINDOW) & 0xffffu);
                     __syncwarp();
                 }
-                const uint32_t pos = base + lane;
-                const bool valid = pos + 4 <= n;
-                const uint32_t v = lds32u(chunk, pos - cb);
-                // lanes without 4 bytes left get a private pseudo-hash so they never group with real ones
-                const uint32_t h = valid ? hash4(v) : (0x10000u + lane);
-                const uint32_t grp = __match_any_sync(CZK_FULL, h);
-                uint32_t d = 0;
-                if (valid) {
+                uint32_t hh[4], din[4];
+                bool val[4], last[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t pos = base4 + 32u * u + lane;
+                    val[u] = pos + 4 <= n;
+                    const uint32_t v = lds32u(chunk, pos - cb);
+                    // lanes without 4 bytes left get a private pseudo-hash so they never group with real ones
+                    hh[u] = val[u] ? hash4(v) : (0x10000u + lane);
+                    const uint32_t grp = __match_any_sync(CZK_FULL, hh[u]);
                     const uint32_t lower = grp & ((1u << lane) - 1u);
-                    if (lower) d = lane - (31u - (uint32_t)__clz((int)lower));  // nearest earlier lane with the same hash
-                    else {
-                        const uint32_t dd = (pos - (uint32_t)head[h]) & 0xffffu;
+                    din[u] = lower ? lane - (31u - (uint32_t)__clz((int)lower)) : 0u;  // nearest earlier lane with the same hash
+                    last[u] = (grp >> lane) <= 1u;                                     // highest lane of its group
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t pos = base4 + 32u * u + lane;
+                    uint32_t d = din[u];
+                    if (val[u] && !d) {
+                        const uint32_t dd = (pos - (uint32_t)head[hh[u]]) & 0xffffu;
                         if (dd >= 1 && dd < CZK_WINDOW && dd <= pos) d = dd;
                     }
+                    if (!val[u]) d = 0;
+                    if (pos < n) pd[pos] = (uint16_t)d;
+                    __syncwarp();
+                    if (val[u] && last[u]) head[hh[u]] = (uint16_t)(pos & 0xffffu);
+                    __syncwarp();
                 }
-                if (pos < n) pd[pos] = (uint16_t)d;
-                __syncwarp();
-                if (valid && (grp >> lane) <= 1u) head[h] = (uint16_t)(pos & 0xffffu);  // highest lane of the group
-                __syncwarp();
             }
         }
     }
