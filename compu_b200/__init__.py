@@ -9,6 +9,6 @@ All compute happens in compu_b200/libcompu_b200.so (hand-written CUDA, C ABI in 
 There is no CPU fallback: without the built library or without an sm_100 device, calls fail loudly.
 """
 from . import decoder, encoder  # noqa: F401
-from .buffer import Buffer, Vec  # noqa: F401
+from .buffer import Buffer, PinnedBuffer, Vec  # noqa: F401
 from .decoder import Decode, DecodeError, DecodeStatus, Decoder, Detection  # noqa: F401
 from .encoder import Encode, EncodeOp, EncodeStatus, Encoder  # noqa: F401

@@ -123,3 +123,37 @@ class Buffer:
         result = encoder.encode_uninit(input, spare, op)
         self.cursor = self.cursor + spare_len - result.output_remain
         return len(input) - result.input_remain, result.status
+
+
+class PinnedBuffer(Buffer):
+    """`Buffer<N>` over page-locked host memory (cz_host_alloc — the pinned analogue of compu_malloc, src/mem.rs:27-49):
+    the batched entry points DMA straight from / to it, no driver staging. Same cursor API as Buffer."""
+
+    def __init__(self, n=1 << 20):
+        from . import _lib
+        assert n >= 128, "Buffer less than 128 bytes makes no sense"
+        self._lib = _lib.lib()
+        self._ptr = self._lib.cz_host_alloc(n)
+        if not self._ptr:
+            raise RuntimeError("compu_b200: cz_host_alloc(%d) failed: %s" % (n, _lib.last_error()))
+        self._buf = np.ctypeslib.as_array(ctypes.cast(self._ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(n,))
+        self.cursor = 0
+
+    def data(self):
+        return self._buf[:self.cursor].tobytes()
+
+    def view(self):
+        """numpy view of the whole pinned array (zero copy)."""
+        return self._buf
+
+    def close(self):
+        if getattr(self, "_ptr", None):
+            self._buf = None
+            self._lib.cz_host_free(ctypes.c_void_p(self._ptr))
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

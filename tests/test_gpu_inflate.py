@@ -145,3 +145,41 @@ def test_mixed_big_and_small_units_vs_oracle(alice):
         ref_outs, ref_st, _ = oracle_inflate(streams, caps, wbits)
         assert_inflate_parity(outs, st, ref_outs, ref_st, "mixed wbits %d" % wbits)
         assert list(cons) == [len(s) for s in streams]
+
+
+def test_pinned_buffer_and_pointer_array_entry(golden, alice):
+    # PinnedBuffer: Buffer<N> over page-locked memory (the pinned analogue of compu_malloc / Buffer<N>)
+    from compu_b200 import PinnedBuffer
+    d = Interface.zlib_cuda(ZlibMode.Gzip)
+    data, comp = golden[1]
+    buf = PinnedBuffer(8192)
+    out = bytearray()
+    inp = comp
+    while True:
+        consumed, status = buf.decode(d, inp)
+        inp = inp[consumed:]
+        out += buf.data()
+        buf.consume()
+        if status == DecodeStatus.Finished:
+            break
+    assert bytes(out) == data
+    buf.close()
+    # cz_inflate_batch_ptrs: the pointer-array form of the batched entry point (SURVEY.md §8b proposal)
+    import ctypes
+    L = _lib.lib()
+    chunks = [alice[i * 10000:(i + 1) * 10000] for i in range(12)] + [b""]
+    streams = [zlib.compress(c, 6) for c in chunks]
+    n = len(streams)
+    ins = [np.frombuffer(s, dtype=np.uint8).copy() for s in streams]
+    outs = [np.zeros(max(1, len(c)), dtype=np.uint8) for c in chunks]
+    in_ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in ins])
+    out_ptrs = (ctypes.c_void_p * n)(*[a.ctypes.data for a in outs])
+    in_lens = (ctypes.c_size_t * n)(*[len(s) for s in streams])
+    out_caps = (ctypes.c_size_t * n)(*[len(c) for c in chunks])
+    out_lens = (ctypes.c_size_t * n)()
+    st = (ctypes.c_int32 * n)()
+    rc = L.cz_inflate_batch_ptrs(n, in_ptrs, in_lens, out_ptrs, out_caps, out_lens, st, 15, 0)
+    _lib.check(rc, "cz_inflate_batch_ptrs")
+    assert list(st) == [2] * n and list(out_lens) == [len(c) for c in chunks]
+    for a, c in zip(outs, chunks):
+        assert a[:len(c)].tobytes() == c
