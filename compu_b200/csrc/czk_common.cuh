@@ -17,6 +17,7 @@
 #endif
 #else
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #define CZ_DYNAMIC_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
 #endif
 

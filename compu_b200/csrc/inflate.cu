@@ -92,6 +92,8 @@ struct ProfRec { cudaEvent_t e0, e1, e2; };
 static std::vector<ProfRec> g_prof;
 static std::mutex g_prof_mu;
 
+static int g_lz_cta = -1, g_lz_spin = -1;
+
 template <int WA, int WB, int H>
 static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams &P, void *d_ws, uint64_t ws_bytes,
                             uint64_t total_out_bytes, size_t n_span) {
@@ -106,13 +108,27 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
     Q.counter_b = (unsigned long long *)((uint8_t *)d_ws + 128);
     Q.meta = (czk::TokMeta *)((uint8_t *)d_ws + two_phase_meta_off());
     Q.tok = (uint32_t *)((uint8_t *)d_ws + two_phase_tok_off(n_span));
+    Q.counter_c = (unsigned long long *)((uint8_t *)d_ws + 192);
+    // phase B of units whose output slot fits the shared-memory tile runs one CTA per unit (CZ_LZ_CTA=0: off)
+    if (g_lz_cta < 0) { const char *e = getenv("CZ_LZ_CTA"); g_lz_cta = e ? atoi(e) : 0; }
+    if (g_lz_spin < 0) { const char *e = getenv("CZ_LZ_SPIN_NS"); g_lz_spin = e ? atoi(e) : 100; }
+    Q.cta_tile = g_lz_cta ? CZK_LZ_TILE : 0;
+    Q.spin_ns = (uint32_t)g_lz_spin;
+    constexpr int WC = 8;
+    auto kc = czk::inflate_lz_cta_kernel<WC, 32 / WC>;
+    auto kc4 = czk::inflate_lz_cta_kernel<4, 8>;
+    const size_t smem_c = czk::inflate_lz_cta_smem_bytes<WC>();
     auto ka = czk::inflate_tok_kernel<WA>;
     auto kb = czk::inflate_lz_kernel<WB, H>;
     const size_t smem = czk::inflate_tok_smem_bytes<WA>();
     static bool configured[64] = {};
-    static int per_sm_a[64], per_sm_b[64];
+    static int per_sm_a[64], per_sm_b[64], per_sm_c[64];
     const int d = ctx->dev & 63;
     if (!configured[d]) {
+        if (!CZ_CUDA(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c))) return CZ_E_MEM;
+        if (!CZ_CUDA(cudaFuncSetAttribute(kc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c))) return CZ_E_MEM;
+        if (!CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c[d], kc, WC * 32, smem_c))) return CZ_E_MEM;
+        if (per_sm_c[d] < 1) { set_error("inflate_lz_cta_kernel does not fit on an SM"); return CZ_E_MEM; }
         if (!CZ_CUDA(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return CZ_E_MEM;
         if (!CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a[d], ka, WA * 32, smem))) return CZ_E_MEM;
         if (!CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b[d], kb, WB * 32, 0))) return CZ_E_MEM;
@@ -142,6 +158,12 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
     } else
     ka<<<(unsigned)ga, WA * 32, smem, st>>>(Q);
     if (g_prof_on) cudaEventRecord(pr.e1, st);
+    if (Q.cta_tile) {
+        uint64_t gc = P.n, gcmax = (uint64_t)ctx->sm_count * per_sm_c[d];
+        if (gc > gcmax) gc = gcmax;
+        if (g_lz_cta == 2) kc4<<<(unsigned)gc, 4 * 32, smem_c, st>>>(Q);
+        else kc<<<(unsigned)gc, WC * 32, smem_c, st>>>(Q);
+    }
     uint64_t gb = (P.n + WB - 1) / WB;
     static int lz_cap = -1;  // experiment knob: CTAs of phase B per SM (fewer streams in flight => their windows fit L2)
     if (lz_cap < 0) { const char *e = getenv("CZ_LZ_CTAS_PER_SM"); lz_cap = e ? atoi(e) : 0; }
@@ -249,6 +271,12 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
 }  // namespace czh
 
 using namespace czh;
+
+extern "C" int cz_tune_inflate_lz(int cta_mode, int spin_ns) {
+    g_lz_cta = cta_mode;
+    g_lz_spin = spin_ns;
+    return 0;
+}
 
 extern "C" uint64_t cz_inflate_workspace_bytes(size_t n, uint64_t total_out_bytes) { return inflate_workspace_bytes(n, total_out_bytes); }
 

@@ -25,9 +25,9 @@ struct LcSlot {
     uint32_t lit_info[16];    // per code length: (offs - first_code) mod 2^16 | (first sorted index holding a symbol >= 256) << 16
     uint16_t dist_base[16];   // offs[len] - first_code[len]  (mod 2^16)
     uint8_t dist_sorted[32];
-    uint8_t pad[32];
+    uint8_t pad[36];          // 452 B = 113 words: an odd word stride, so the 32 lanes' slots start in 32 different banks
 };
-static_assert(sizeof(LcSlot) == 448, "LcSlot layout");
+static_assert(sizeof(LcSlot) == 452, "LcSlot layout");
 
 __device__ __forceinline__ uint8_t *lc_lens(LcSlot &sm) { return (uint8_t *)&sm + 128; }
 
@@ -40,10 +40,23 @@ __host__ __device__ inline uint32_t lc_len_info(uint32_t c) {
     return base | (e << 9);
 }
 
+// The 15 code limits of one code (left-justified to 16 bits, non-decreasing; 65536 = "no code can reach this") live in 8
+// registers. A limit for length L <= 14 has its low two bits clear, so `v >= limit` can be decided on the 14-bit values
+// v >> 2 and limit >> 2; biased by 0x400 these are bit patterns of finite, normal fp16 numbers (0x0400..0x4400) whose
+// order as numbers is their order as integers. pk[j] (j < 7) holds the limits of lengths 2j+1 (low half) and 2j+2 (high
+// half) in that form: one HSET2 compares two limits, and the FP16 pipe does the counting instead of the integer ALU.
+// pk[7] is the limit of length 15 as a plain integer.
+#define CZK_LC_PK_NONE 0x44004400u  // both halves "unreachable"
+__device__ __forceinline__ void lc_limits_reset(uint32_t (&pk)[8]) {
+#pragma unroll
+    for (int i = 0; i < 7; i++) pk[i] = CZK_LC_PK_NONE;
+    pk[7] = 0x10000u;
+}
+
 // Warp-cooperative: builds slot `sm` (sorted symbols + base offsets) from the code lengths in its scratch and hands the
-// 2x15 code limits to lane `owner` (left-justified to 16 bits, non-decreasing; 65536 = "no code can reach this").
+// 2x15 code limits to lane `owner` in the packed form above.
 __device__ __forceinline__ int lc_build(LcSlot &sm, uint32_t nlit, uint32_t ndist, uint32_t *wcnt, uint32_t *wrun, uint32_t lane,
-                               uint32_t owner, uint32_t (&llim)[15], uint32_t (&dlim)[15]) {
+                               uint32_t owner, uint32_t (&llim)[8], uint32_t (&dlim)[8]) {
     const uint8_t *lens = lc_lens(sm);
     uint32_t ll[9];
 #pragma unroll
@@ -66,6 +79,9 @@ __device__ __forceinline__ int lc_build(LcSlot &sm, uint32_t nlit, uint32_t ndis
         int left = 1;
         uint32_t code = 0, off = 0, maxlen = 0, my_first = 0, my_off = 0;
         bool over = false;
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) pk[i] = 0;
 #pragma unroll
         for (uint32_t len = 1; len <= 15; len++) {
             uint32_t c = wcnt[len];
@@ -73,10 +89,16 @@ __device__ __forceinline__ int lc_build(LcSlot &sm, uint32_t nlit, uint32_t ndis
             if (left < 0) over = true;
             if (lane == len) { my_first = code; my_off = off; }
             uint32_t lim = (code + c) << (16 - len);
-            if (lane == owner) { if (is_dist) dlim[len - 1] = lim; else llim[len - 1] = lim; }
+            if (lim > 0x10000u) lim = 0x10000u;  // over-subscribed sets are rejected below; keep the packed fields in range
+            if (len < 15) pk[(len - 1) >> 1] |= ((lim >> 2) + 0x400u) << (16 * ((len - 1) & 1));
+            else pk[7] = lim;
             code = (code + c) << 1;
             off += c;
             if (c) maxlen = len;
+        }
+        if (lane == owner) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) { if (is_dist) dlim[i] = pk[i]; else llim[i] = pk[i]; }
         }
         if (over || (left > 0 && maxlen > 1)) rc = ST_E_DATA;  // zlib inflate_table(): over-subscribed / incomplete set
         if (lane >= 1 && lane < 16) {
@@ -110,11 +132,25 @@ __device__ __forceinline__ int lc_build(LcSlot &sm, uint32_t nlit, uint32_t ndis
 }
 
 // code length of the codeword at the top of the 16-bit left-justified window v: 1 + number of limits <= v (16 = invalid)
-__device__ __forceinline__ uint32_t lc_code_len(uint32_t v, const uint32_t (&lim)[15]) {
-    uint32_t len = 1;
+__device__ __forceinline__ uint32_t lc_code_len(uint32_t v, const uint32_t (&pk)[8]) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t vv = (v >> 2) * 0x10001u + 0x04000400u;
+    const __half2 hv = *reinterpret_cast<const __half2 *>(&vv);
+    __half2 c[7];
 #pragma unroll
-    for (int i = 0; i < 15; i++) len += v >= lim[i] ? 1u : 0u;
-    return len;
+    for (int i = 0; i < 7; i++) c[i] = __hge2(hv, *reinterpret_cast<const __half2 *>(&pk[i]));  // 1.0 where v >= limit
+    const uint32_t magic = 0x64006400u;  // (1024, 1024): 1024 + k has the bit pattern 0x6400 + k
+    __half2 s = __hadd2(__hadd2(__hadd2(c[0], c[1]), __hadd2(c[2], c[3])),
+                        __hadd2(__hadd2(c[4], c[5]), __hadd2(c[6], *reinterpret_cast<const __half2 *>(&magic))));
+    const uint32_t sb = *reinterpret_cast<const uint32_t *>(&s);
+    return 1u + ((sb + (sb >> 16)) & 0xfu) + (v >= pk[7] ? 1u : 0u);
+#else
+    uint32_t len = 1;
+    const uint32_t v14 = (v >> 2) + 0x400u;
+#pragma unroll
+    for (int i = 0; i < 14; i++) len += v14 >= ((pk[i >> 1] >> (16 * (i & 1))) & 0xffffu) ? 1u : 0u;
+    return len + (v >= pk[7] ? 1u : 0u);
+#endif
 }
 
 // Lane-local dynamic header parse (RFC 1951 §3.2.7) into lc_lens(sm); 0, ST_E_DATA or 100 (= input exhausted).
@@ -209,9 +245,8 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lc_kernel(InflateParams P)
 
     BitReader br;
     br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.total = 0;
-    uint32_t llim[15], dlim[15];
-#pragma unroll
-    for (int i = 0; i < 15; i++) { llim[i] = 0x10000u; dlim[i] = 0x10000u; }
+    uint32_t llim[8], dlim[8];
+    lc_limits_reset(llim); lc_limits_reset(dlim);
     int st = SS_IDLE;
     uint32_t unit = 0;
     const uint8_t *in_base = nullptr;

@@ -20,8 +20,8 @@
 // Token words (uint32):
 //   match    bit31 = 0           bits 0-8 length (1..258, may be cut by the output capacity), bits 9-24 distance (1..32768)
 //   literals bits 31-30 = 10     bits 24-25 count (1..3), bits 0-23 the bytes, first byte lowest
-//   stored   bits 31-30 = 11     three words: low 16 bits of word 0 = length, low 30 bits of words 1 and 2 = byte offset
-//                                of the run inside the unit's input (low, high)
+//   stored   bits 31-30 = 11     three words: word 0 (bit 29 = 0) holds the length in its low 16 bits; words 1 and 2 (bit 29 = 1,
+//                                "tail" words) hold the byte offset of the run inside the unit's input, 29 bits each (low, high)
 // Worst case one word per output byte (1-byte stored blocks are written as literal tokens), hence the 4 x capacity
 // token area per unit.
 //
@@ -45,12 +45,16 @@ struct TwoPhaseParams {
     TokMeta *meta;               // n
     unsigned long long *counter_b;  // phase B work counter, zero before launch
     int32_t count_only;          // phase A only: no tokens are written, TokMeta.out_len / status / in_consumed are the result
+    unsigned long long *counter_c;  // work counter of inflate_lz_cta_kernel, zero before launch
+    uint32_t cta_tile;           // != 0: units whose output slot is at most this many bytes belong to inflate_lz_cta_kernel
+    uint32_t spin_ns;            // inflate_lz_cta_kernel: back-off of a warp that found no ready token
 };
 
 __host__ __device__ inline uint64_t tok_word_off(uint64_t out_off, uint64_t unit) { return out_off + 8 * unit; }
 
 #define CZK_TOK_LIT 0x80000000u
 #define CZK_TOK_STORED 0xC0000000u
+#define CZK_TOK_TAIL 0x20000000u
 #define CZK_LZ_SHORT 12  // phase B (token-parallel): matches up to this long are copied by their own lane (8/12/16/24/32 measured: 33.9/32.6/34.0/35.5/38.0 ms)
 
 template <int WARPS>
@@ -68,9 +72,8 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
 
     BitReader br;
     br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.total = 0;
-    uint32_t llim[15], dlim[15];
-#pragma unroll
-    for (int i = 0; i < 15; i++) { llim[i] = 0x10000u; dlim[i] = 0x10000u; }
+    uint32_t llim[8], dlim[8];
+    lc_limits_reset(llim); lc_limits_reset(dlim);
     int st = SS_IDLE;
     uint32_t unit = 0;
     const uint8_t *in_base = nullptr;
@@ -166,10 +169,15 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
         }
 
         // ---- (5) decode into tokens, lane-local, CZK_LC_BUDGET symbols per visit
+        // One visit of the loop consumes at most 48 bits and produces at most 258 bytes. While three more input words and
+        // 258 bytes of capacity remain, none of the end-of-input / end-of-slot tests can fire: they are evaluated only when
+        // `slow` is set (the last ~12 bytes of input or the last 258 bytes of the slot).
         if (st == SS_DECODE) {
             int budget = CZK_LC_BUDGET;
+            const int64_t pos_safe = (int64_t)cap - 258;
             while (budget-- > 0) {
                 br.refill();
+                const bool slow = !(br.widx + 3 <= br.wend && (int64_t)pos <= pos_safe);
                 uint32_t v = __brev((uint32_t)br.buf) >> 16;
                 uint32_t cl = lc_code_len(v, llim);
                 if (cl > 15) {  // no code matches (incomplete set) — or zero bits past a truncated input
@@ -182,15 +190,17 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
                 uint32_t sym = my.lit_sorted[idx < 288 ? idx : 287] | (idx >= (info >> 16) ? 256u : 0u);
                 br.skip(cl);
                 if (sym < 256) {  // literal
-                    if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
-                    if (pos >= cap) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
+                    if (slow) {
+                        if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
+                        if (pos >= cap) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
+                    }
                     pos++;
                     lit |= sym << (8 * nlit);
                     if (++nlit == 3) { CZK_PUT(CZK_TOK_LIT | (3u << 24) | lit); lit = 0; nlit = 0; }
                     continue;
                 }
                 if (sym == 256) {  // end of block
-                    if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
+                    if (slow && br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
                     if (bfinal) { result = ST_FINISHED; st = SS_TRAILER; } else st = SS_BLOCK;
                     break;
                 }
@@ -217,12 +227,14 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
                 uint32_t deb = dsym < 2 ? 0 : (dsym >> 1) - 1;
                 uint32_t dist = ((dsym < 2 ? dsym : 2 + (dsym & 1)) << deb) + 1 + br.peek(deb);
                 br.skip(deb);
-                if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
-                // zlib order (inflate.c MATCH): output space first, then "invalid distance too far back"
-                if (pos >= cap) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
-                if ((uint64_t)dist > pos) { result = ST_E_DATA; st = SS_FINISH; break; }
                 uint32_t n = len;
-                if (pos + n > cap) n = (uint32_t)(cap - pos);
+                if (slow) {
+                    if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
+                    // zlib order (inflate.c MATCH): output space first, then "invalid distance too far back"
+                    if (pos >= cap) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
+                    if (pos + n > cap) n = (uint32_t)(cap - pos);
+                }
+                if ((uint64_t)dist > pos) { result = ST_E_DATA; st = SS_FINISH; break; }
                 CZK_FLUSH_LIT();
                 CZK_PUT(n | (dist << 9));
                 pos += n;
@@ -240,8 +252,8 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
             if (n > 8) {
                 CZK_FLUSH_LIT();
                 CZK_PUT(CZK_TOK_STORED | n);
-                CZK_PUT(CZK_TOK_STORED | (uint32_t)(ipos & 0x3fffffffu));
-                CZK_PUT(CZK_TOK_STORED | (uint32_t)(ipos >> 30));
+                CZK_PUT(CZK_TOK_STORED | CZK_TOK_TAIL | (uint32_t)(ipos & 0x1fffffffu));
+                CZK_PUT(CZK_TOK_STORED | CZK_TOK_TAIL | (uint32_t)(ipos >> 29));
             } else {
                 for (uint32_t k = 0; k < n; k++) {
                     lit |= (uint32_t)in_base[ipos + k] << (8 * nlit);
@@ -318,8 +330,9 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lz_kernel(TwoPhaseParams Q
         u64 = __shfl_sync(CZK_FULL, u64, 0);
         if (u64 >= P.n) break;
         const uint32_t unit = P.ids ? P.ids[u64] : (uint32_t)u64;
-        const TokMeta m = Q.meta[unit];
         const uint64_t o0 = P.out_off[unit];
+        if (Q.cta_tile && P.out_off[unit + 1] - o0 <= Q.cta_tile) continue;  // resolved by inflate_lz_cta_kernel
+        const TokMeta m = Q.meta[unit];
         uint8_t *ob = P.out + o0;
         const uint8_t *ib = P.in + P.in_off[unit];
         const uint32_t *tok = Q.tok + tok_word_off(o0 - P.out_off[0], unit);
@@ -491,7 +504,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lz_kernel(TwoPhaseParams Q
                 // a stored run: three marked words starting at ti
                 const uint32_t w0 = tok[ti], w1 = tok[ti + 1], w2 = tok[ti + 2];
                 const uint32_t n = w0 & 0xffffu;
-                const uint64_t ipos = (uint64_t)(w1 & 0x3fffffffu) | ((uint64_t)(w2 & 0x3fffffffu) << 30);
+                const uint64_t ipos = (uint64_t)(w1 & 0x1fffffffu) | ((uint64_t)(w2 & 0x1fffffffu) << 29);
                 for (uint32_t k = lane; k < n; k += 32) ob[opos + k] = ib[ipos + k];
                 __syncwarp();
                 opos += n;
@@ -531,6 +544,311 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lz_kernel(TwoPhaseParams Q
                 if (m.wrap == 2 && m.expect != crc) status = ST_E_DATA;
             }
             P.out_lens[unit] = opos;
+            P.statuses[unit] = status;
+            if (P.checks) { P.checks[2 * unit] = adler; P.checks[2 * unit + 1] = crc; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Phase B for units whose output slot fits a shared-memory tile: one CTA per unit.
+//
+// The whole output of the unit (<= 64 KiB) is assembled in shared memory, so back-references cost a shared-memory
+// access instead of an L2/DRAM round trip, and the finished tile leaves with 16-byte coalesced stores. W warps work
+// on one unit at a time, W*K*32 tokens per chunk (lane = token, K tokens per lane):
+//   * a block scan of the token lengths gives every token its output position;
+//   * literals, stored runs and matches whose source lies below the chunk are copied at once;
+//   * a match that reads bytes produced by this chunk waits for exactly the tokens that produce them: every token sets
+//     a bit in a done mask when its bytes are in the tile, and a position -> token map with one entry per 8 output bytes
+//     turns the source range [lo, e) into a (slightly widened) token range [a, b], b < own index. Dependencies only point
+//     to lower token indices, so the lowest unfinished token is always ready and the warps never wait on a barrier while
+//     they resolve — they poll the done mask. Deflate text needs ~7 dependent levels per 1 024 tokens this way, against
+//     ~23 rounds with a single completed-prefix frontier.
+// Adler-32 is computed from the tile, CRC-32 from the freshly stored output; W partial values are folded with the combine
+// identities.
+#define CZK_LZ_TILE 65536u
+#define CZK_LZ_SPAN 16384u  // output bytes one chunk may start tokens in (8 bytes per map entry)
+
+template <int W>
+constexpr size_t inflate_lz_cta_smem_bytes() { return CZK_LZ_TILE + 16 + (256 + 34) * 4 + 8 + 3 * 32 * 4 + 4 * 8 * 4 + CZK_LZ_SPAN / 8 * 2; }
+
+__device__ __forceinline__ bool lz_deps_done(const volatile uint32_t *dmask, uint32_t dep) {
+    const uint32_t a = dep & 0xffffu, b = dep >> 16;
+    const uint32_t wa = a >> 5, wb = b >> 5;
+    const uint32_t lo_m = 0xffffffffu << (a & 31), hi_m = 0xffffffffu >> (31 - (b & 31));
+    if (wa == wb) { const uint32_t mm = lo_m & hi_m; return (dmask[wa] & mm) == mm; }
+    if ((dmask[wa] & lo_m) != lo_m) return false;
+    if ((dmask[wb] & hi_m) != hi_m) return false;
+    for (uint32_t w = wa + 1; w < wb; w++) if (dmask[w] != 0xffffffffu) return false;
+    return true;
+}
+
+template <int W, int K>
+__global__ void __launch_bounds__(W * 32, 3) inflate_lz_cta_kernel(TwoPhaseParams Q) {
+    static_assert(W * K == 32, "the block scan keeps one token group per lane");
+    constexpr uint32_t T = W * K * 32;
+    constexpr int SHORT = CZK_LZ_SHORT;
+    constexpr uint32_t DEP_NONE = 0xffffffffu;
+    const InflateParams &P = Q.base;
+    CZ_DYNAMIC_SMEM(smem_raw);
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t *tile_mem = smem_raw;
+    uint32_t *crc_tab = (uint32_t *)(smem_raw + CZK_LZ_TILE + 16);
+    unsigned long long *s_u = (unsigned long long *)(crc_tab + 256 + 34);
+    volatile uint32_t *gtot = (volatile uint32_t *)(s_u + 1);  // [32] bytes of every token group
+    volatile uint32_t *dmask = gtot + 32;                       // [32] done bits, one word per token group
+    volatile uint32_t *gtot2 = dmask + 32;                      // [32] clipped chunks: bytes | tokens << 20 of every group
+    uint32_t *part = (uint32_t *)(gtot2 + 32);                  // [W][4]: adler, crc (shifted to the end), bytes
+    uint16_t *map8 = (uint16_t *)(part + 4 * W);                // [SPAN / 8] token that covers chunk byte 8 q
+    if (P.crc)
+        for (uint32_t i = tid; i < 256 + 34; i += W * 32) crc_tab[i] = i < 256 ? P.crc->table[i] : P.crc->pow128[i - 256];
+
+    for (;;) {
+        __syncthreads();  // the previous unit is finished (tile, s_u, part)
+        if (tid == 0) *s_u = atomicAdd(Q.counter_c, 1ull);
+        __syncthreads();
+        const unsigned long long u64 = *s_u;
+        if (u64 >= P.n) break;
+        const uint32_t unit = P.ids ? P.ids[u64] : (uint32_t)u64;
+        const uint64_t o0 = P.out_off[unit];
+        const uint64_t cap = P.out_off[unit + 1] - o0;
+        if (cap > CZK_LZ_TILE) continue;  // resolved by inflate_lz_kernel
+        const TokMeta m = Q.meta[unit];
+        uint8_t *ob = P.out + o0;
+        const uint8_t *ib = P.in + P.in_off[unit];
+        const uint32_t *tok = Q.tok + tok_word_off(o0 - P.out_off[0], unit);
+        const uint32_t ntok = m.ntok;
+        const uint32_t mis = (uint32_t)((uintptr_t)ob & 15);
+        uint8_t *tile = tile_mem + mis;  // tile byte k and output byte k have the same alignment
+        uint32_t opos = 0;
+        bool bad = false;
+        uint32_t ti0 = 0;
+        while (ti0 < ntok) {
+            uint32_t t[K], tl[K], rel[K];
+            // ---- tokens, lengths, scan inside every group of 32
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const uint32_t i = ti0 + (warp * K + k) * 32 + lane;
+                t[k] = i < ntok ? tok[i] : (CZK_TOK_STORED | CZK_TOK_TAIL);
+                const uint32_t top = t[k] >> 29;  // 0 match, 4/5 literals, 6 stored run, 7 tail word of a stored run / padding
+                tl[k] = top < 4 ? (t[k] & 0x1ffu) : top < 6 ? ((t[k] >> 24) & 3u) : top == 6 ? (t[k] & 0xffffu) : 0u;
+                uint32_t incl = tl[k];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(CZK_FULL, incl, d);
+                    if ((int)lane >= d) incl += v;
+                }
+                rel[k] = incl - tl[k];
+                if (lane == 31) gtot[warp * K + k] = incl;
+            }
+            __syncthreads();  // (A) every warp has left the previous chunk; group totals are visible
+            uint32_t gsum = gtot[lane];
+            uint32_t gincl = gsum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_up_sync(CZK_FULL, gincl, d);
+                if ((int)lane >= d) gincl += v;
+            }
+            const uint32_t gexcl = gincl - gsum;
+            uint32_t chunk_bytes = __shfl_sync(CZK_FULL, gincl, 31);
+            uint32_t nt = T;
+#pragma unroll
+            for (int k = 0; k < K; k++) rel[k] += __shfl_sync(CZK_FULL, gexcl, warp * K + k);
+            const bool clipped = chunk_bytes > CZK_LZ_SPAN;
+            if (clipped) {
+                // tokens that start beyond the span wait for the next chunk
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    const bool in = rel[k] < CZK_LZ_SPAN;
+                    if (!in) tl[k] = 0;
+                    const uint32_t cnt = __popc(__ballot_sync(CZK_FULL, in));
+                    const uint32_t bytes = __reduce_add_sync(CZK_FULL, tl[k]);
+                    if (lane == 0) gtot2[warp * K + k] = bytes | (cnt << 20);
+                }
+            }
+            // ---- position -> token map, done bits of the tokens that produce nothing
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const uint32_t j = (warp * K + k) * 32 + lane;
+                if (tl[k]) {
+                    uint32_t p1 = rel[k] + tl[k];
+                    if (p1 > CZK_LZ_SPAN) p1 = CZK_LZ_SPAN;
+                    for (uint32_t q = (rel[k] + 7) >> 3; 8 * q < p1; q++) map8[q] = (uint16_t)j;
+                }
+                const uint32_t dm = __ballot_sync(CZK_FULL, tl[k] == 0);
+                if (lane == 0) dmask[warp * K + k] = dm;
+            }
+            __syncthreads();  // (B) map, done mask (and the clipped totals) are visible
+            if (clipped) {
+                const uint32_t g2 = gtot2[lane];
+                const uint32_t s2 = __reduce_add_sync(CZK_FULL, g2);
+                chunk_bytes = s2 & 0xfffffu;
+                nt = s2 >> 20;
+            }
+            if (opos + chunk_bytes > CZK_LZ_TILE) { bad = true; break; }  // cannot happen with tokens of inflate_tok_kernel
+            const uint32_t map_end = chunk_bytes < CZK_LZ_SPAN ? chunk_bytes : CZK_LZ_SPAN;
+
+            // ---- dependencies
+            uint32_t dep[K];
+            uint32_t pend = 0;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                dep[k] = DEP_NONE;
+                const uint32_t j = (warp * K + k) * 32 + lane;
+                if (tl[k]) pend |= 1u << k;
+                if (tl[k] && (t[k] >> 31) == 0) {
+                    const uint32_t dist = (t[k] >> 9) & 0xffffu;
+                    const int s = (int)rel[k] - (int)dist;                 // chunk-relative source start (may be negative)
+                    int e = s + (int)tl[k];
+                    if (e > (int)rel[k]) e = (int)rel[k];                   // a self-overlapping match repeats its own start
+                    if (e > 0) {
+                        const uint32_t lo = s > 0 ? (uint32_t)s : 0u;
+                        const uint32_t a = map8[lo >> 3];
+                        const uint32_t qe = (((uint32_t)e - 1u) >> 3) + 1u;
+                        uint32_t b = 8 * qe < map_end ? (uint32_t)map8[qe] : j - 1;
+                        if (b > j - 1) b = j - 1;
+                        dep[k] = a | (b << 16);
+                    }
+                }
+            }
+
+            // ---- resolution
+            uint8_t *obp = tile + opos;
+            for (;;) {
+                bool progress = false;
+#pragma unroll
+                for (int k = 0; k < K; k++) {
+                    bool ready = false;
+                    if ((pend >> k) & 1u) ready = dep[k] == DEP_NONE || lz_deps_done(dmask, dep[k]);
+                    const uint32_t rm = __ballot_sync(CZK_FULL, ready);
+                    if (!rm) continue;
+                    __threadfence_block();  // bytes of the tokens whose done bits were just read
+                    const uint32_t tk = t[k], len = tl[k];
+                    const uint32_t top = tk >> 29;
+                    const uint32_t dist = (tk >> 9) & 0xffffu;
+                    const bool is_match = top < 4, is_run = top == 6;
+                    const bool coop = ready && ((is_match && (len > (uint32_t)SHORT || dist < len)) || is_run);
+                    if (ready && !coop) {
+                        uint8_t *d = obp + rel[k];
+                        if (!is_match) {
+                            d[0] = (uint8_t)tk;
+                            if (len > 1) d[1] = (uint8_t)(tk >> 8);
+                            if (len > 2) d[2] = (uint8_t)(tk >> 16);
+                        } else {
+                            const uint8_t *sp = d - dist;
+                            uint32_t bb[SHORT];
+#pragma unroll
+                            for (int x = 0; x < SHORT; x++) bb[x] = x < (int)len ? sp[x] : 0u;
+#pragma unroll
+                            for (int x = 0; x < SHORT; x++) if (x < (int)len) d[x] = (uint8_t)bb[x];
+                        }
+                    }
+                    uint32_t cm = __ballot_sync(CZK_FULL, coop);
+                    while (cm) {
+                        const int sl = __ffs((int)cm) - 1;
+                        cm &= cm - 1;
+                        const uint32_t Ln = __shfl_sync(CZK_FULL, len, sl), D = __shfl_sync(CZK_FULL, dist, sl);
+                        const uint32_t P0 = __shfl_sync(CZK_FULL, rel[k], sl);
+                        const uint32_t topx = __shfl_sync(CZK_FULL, top, sl);
+                        uint8_t *d = obp + P0;
+                        if (topx == 6) {
+                            // stored run: the bytes come from the unit's input
+                            const uint32_t i = ti0 + (warp * K + k) * 32 + (uint32_t)sl;
+                            const uint32_t w1 = tok[i + 1], w2 = tok[i + 2];
+                            const uint8_t *src = ib + ((uint64_t)(w1 & 0x1fffffffu) | ((uint64_t)(w2 & 0x1fffffffu) << 29));
+                            for (uint32_t x = lane; x < Ln; x += 32) d[x] = src[x];
+                        } else {
+                            const uint8_t *sp = d - D;
+                            if (D >= Ln) {
+                                for (uint32_t x = lane; x < Ln; x += 32) d[x] = sp[x];
+                            } else if (D >= 32) {
+                                for (uint32_t x0 = 0; x0 < Ln; x0 += 32) {
+                                    const uint32_t x = x0 + lane;
+                                    if (x < Ln) d[x] = sp[x];
+                                    __syncwarp();
+                                }
+                            } else {
+                                uint32_t r = lane % D;
+                                const uint32_t stepD = 32u % D;
+                                for (uint32_t x = lane; x < Ln; x += 32) {
+                                    d[x] = sp[r];
+                                    r += stepD;
+                                    if (r >= D) r -= D;
+                                }
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    __threadfence_block();  // the bytes are in the tile before the done bits
+                    if (lane == 0) atomicOr((uint32_t *)&dmask[warp * K + k], rm);
+                    if (ready) pend &= ~(1u << k);
+                    progress = true;
+                }
+                if (!__any_sync(CZK_FULL, pend != 0)) break;
+#if defined(__CUDA_ARCH__)
+                if (!progress && Q.spin_ns) __nanosleep(Q.spin_ns);
+#endif
+            }
+            opos += chunk_bytes;
+            ti0 += nt;
+        }
+        __syncthreads();  // the tile is complete
+
+        // ---- tile -> output, 16 bytes per lane where the output address is aligned
+        const uint32_t total = opos;
+        {
+            uint32_t head = mis ? 16u - mis : 0u;
+            if (head > total) head = total;
+            const uint32_t nvec = (total - head) >> 4;
+            const uint4 *sv = (const uint4 *)(tile + head);
+            uint4 *dv = (uint4 *)(ob + head);
+            for (uint32_t v = tid; v < nvec; v += W * 32) dv[v] = sv[v];
+            if (tid < head) ob[tid] = tile[tid];
+            for (uint32_t x = head + nvec * 16 + tid; x < total; x += W * 32) ob[x] = tile[x];
+        }
+        // ---- checksums: W slices, folded by thread 0
+        const bool by_kind = P.segment_mode || (P.checks && m.wrap == 0);
+        const bool want_adler = by_kind ? (P.check_kind & 1) : m.wrap == 1;
+        const bool want_crc = by_kind ? (P.check_kind & 2) : m.wrap == 2;
+        if (want_adler || want_crc) {
+            const uint32_t q = ((total + W - 1) / W + 127) & ~127u;
+            const uint32_t b0 = warp * q < total ? warp * q : total;
+            const uint32_t n = total - b0 < q ? total - b0 : q;
+            uint32_t a = 1, c = 0;
+            if (want_adler)
+                for (uint32_t o = 0; o < n; o += 8192) a = warp_adler32(a, tile + b0 + o, n - o < 8192 ? n - o : 8192, lane);
+            if (want_crc) {
+                __syncthreads();  // the output bytes of every warp are stored
+                const uint8_t *gp = ob + b0;
+                uint32_t o = 0;
+                while (n - o >= 128) {
+                    uint32_t kk = (n - o) >> 7;
+                    if (kk > 32) kk = 32;
+                    c = warp_crc32_pieces(c, gp + o, kk, crc_tab, crc_tab + 256, lane);
+                    o += kk * 128;
+                }
+                if (lane == 0) {
+                    if (o < n) c = crc32_serial(c, gp + o, n - o, crc_tab);
+                    c = crc_mulmod(crc_xpow8n(total - (b0 + n)), c);  // shifted to the end of the unit
+                }
+            }
+            if (lane == 0) { part[4 * warp] = a; part[4 * warp + 1] = c; part[4 * warp + 2] = n; }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t adler = 1, crc = 0;
+            if (want_adler) {
+                adler = part[0];
+                for (int w = 1; w < W; w++) adler = adler32_combine_u(adler, part[4 * w], part[4 * w + 2]);
+            }
+            if (want_crc)
+                for (int w = 0; w < W; w++) crc ^= part[4 * w + 1];
+            int status = bad ? (int)ST_E_DATA : m.status;
+            if (status == ST_FINISHED && !P.segment_mode) {
+                if (m.wrap == 1 && m.expect != adler) status = ST_E_DATA;  // "incorrect data check"
+                if (m.wrap == 2 && m.expect != crc) status = ST_E_DATA;
+            }
+            P.out_lens[unit] = total;
             P.statuses[unit] = status;
             if (P.checks) { P.checks[2 * unit] = adler; P.checks[2 * unit + 1] = crc; }
         }

@@ -137,6 +137,11 @@ int cz_inflate_segmented(const uint8_t *in, uint64_t len, uint8_t *out, uint64_t
 /* Tuning knob (experiments): selects an inflate kernel variant; see compu_b200/csrc/inflate.cu. Default from CZ_INFLATE_CFG
    or -2,14 (two-phase: lane-per-stream token decode with 14 warps per SM, then warp-per-stream LZ77 resolution). */
 int cz_tune_inflate(int slots_per_warp, int warps_per_cta);
+/* Tuning knob (experiments): phase B of the two-phase inflate for units whose output slot is at most 64 KiB.
+   cta_mode 0: warp per unit, output in global memory (inflate_lz_kernel); 1 / 2: one CTA of 8 / 4 warps per unit, output
+   assembled in a shared-memory tile (inflate_lz_cta_kernel); spin_ns: back-off of a warp that found no ready token.
+   Defaults from CZ_LZ_CTA / CZ_LZ_SPIN_NS. */
+int cz_tune_inflate_lz(int cta_mode, int spin_ns);
 
 /* Scratch bytes cz_inflate_batch_device needs for n streams whose output slots total total_out_bytes
    (= d_out_offsets[n] - d_out_offsets[0]; the token area of the two-phase kernel is 4 bytes per output byte). */

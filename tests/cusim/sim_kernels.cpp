@@ -33,15 +33,20 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
         case 32: run_inflate<32, 1>(P, grid); break;
         case -1: cusim::launch(grid, 2 * 32, inflate_lc_smem_bytes<2>(), inflate_lc_kernel<2>, P); break;
         case -2:
-        case -3: {
+        case -3:
+        case -4: {
             const uint64_t total_out = out_off[n] - out_off[0];
             std::vector<uint32_t> tok(total_out + 8 * n + 64, 0xDEADBEEFu);
             std::vector<TokMeta> meta(n);
-            unsigned long long counter_b = 0;
+            unsigned long long counter_b = 0, counter_c = 0;
             TwoPhaseParams Q;
             Q.base = P; Q.tok = tok.data(); Q.meta = meta.data(); Q.counter_b = &counter_b; Q.count_only = 0;
+            Q.counter_c = &counter_c; Q.cta_tile = D == -4 ? CZK_LZ_TILE : 0; Q.spin_ns = 0;
             cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2>, Q);
-            if (D == -3) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 0>, Q);
+            if (D == -4) {
+                cusim::launch(grid, 8 * 32, inflate_lz_cta_smem_bytes<8>(), inflate_lz_cta_kernel<8, 4>, Q);
+                cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 0>, Q);
+            } else if (D == -3) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 0>, Q);
             else if (seed % 3 == 0) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 4>, Q);
             else if (seed % 3 == 1) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 2>, Q);
             else cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 0>, Q);

@@ -183,3 +183,28 @@ def test_pinned_buffer_and_pointer_array_entry(golden, alice):
     assert list(st) == [2] * n and list(out_lens) == [len(c) for c in chunks]
     for a, c in zip(outs, chunks):
         assert a[:len(c)].tobytes() == c
+
+
+def test_cta_tile_cases_vs_oracle(alice):
+    """Units around the 64 KiB shared-memory tile of inflate_lz_cta_kernel: exact fits, odd slot sizes (misaligned output
+    offsets), stored runs, long runs (clipped chunks), units beyond the tile (inflate_lz_kernel), all three containers."""
+    import random
+    from helpers import make_data
+    rng = random.Random(4242)
+    cases = [(0, 65536, 6), (1, 65536, 6), (2, 65536, 6), (3, 65535, 9), (4, 60001, 6), (0, 65536, 1), (4, 65536, 0),
+             (0, 70000, 6), (1, 33333, 6), (0, 3, 6), (0, 0, 6), (2, 65536, 9), (3, 16385, 6), (4, 65521, 3)] * 8
+    L = _lib.lib()
+    try:
+        for wbits in (15, 31, -15):
+            datas = [make_data(rng, kind, n, alice) for kind, n, _ in cases]
+            streams = [zcomp(d, lvl, wbits) for d, (_, _, lvl) in zip(datas, cases)]
+            caps = [len(d) for d in datas]
+            ref_outs, ref_st, _ = oracle_inflate(streams, caps, wbits)
+            for mode in (0, 1, 2):
+                L.cz_tune_inflate_lz(mode, 100)
+                outs, st, lens, cons = batch.inflate_batch(streams, caps, wbits)
+                assert_inflate_parity(outs, st, ref_outs, ref_st, "cta mode %d wbits %d" % (mode, wbits))
+                assert (st == 2).all()
+                assert list(cons) == [len(s) for s in streams]
+    finally:
+        L.cz_tune_inflate_lz(0, 100)

@@ -6,7 +6,7 @@ import simlib
 from helpers import assert_inflate_parity, fuzz_cases, oracle_inflate, zcomp
 
 
-@pytest.mark.parametrize("D", [1, 4, 32, -9, -8, -1, -2, -3])
+@pytest.mark.parametrize("D", [1, 4, 32, -9, -8, -1, -2, -3, -4])
 def test_sim_golden_gzip(golden, D):
     streams = [c for _, c in golden]
     caps = [len(d) for d, _ in golden]
@@ -20,7 +20,7 @@ def test_sim_golden_gzip(golden, D):
 def test_sim_fuzz_vs_oracle(alice, wbits):
     datas, streams, caps = fuzz_cases(100 + wbits, wbits, 40, alice, sizes=(0, 1, 2, 5, 100, 1000, 5000, 20000))
     ref_outs, ref_st, _ = oracle_inflate(streams, caps, wbits)
-    for D in (1, 8, -9, -1, -2, -3):
+    for D in (1, 8, -9, -1, -2, -3, -4):
         outs, st, ol, cons, _ = simlib.sim_inflate(streams, caps, wbits, D=D, seed=wbits + D)
         assert_inflate_parity(outs, st, ref_outs, ref_st, "wbits %d D %d" % (wbits, D))
 
@@ -34,9 +34,33 @@ def test_sim_segment_mode_checks(alice):
         c = zlib.compressobj(6, zlib.DEFLATED, -15)
         segs.append(c.compress(d) + c.flush(zlib.Z_FULL_FLUSH))
         datas.append(d)
-    for D in (4, -9, -1, -2, -3):
+    for D in (4, -9, -1, -2, -3, -4):
         outs, st, ol, cons, ck = simlib.sim_inflate(segs, [len(d) for d in datas], -15, segment_mode=1, check_kind=3, D=D)
         assert list(st) == [2] * 6
         for i, d in enumerate(datas):
             assert outs[i] == d
             assert ck[2 * i] == zlib.adler32(d) and ck[2 * i + 1] == zlib.crc32(d)
+
+
+def test_sim_cta_tile_cases(alice):
+    """Units around the 64 KiB shared-memory tile of inflate_lz_cta_kernel: exact fits, odd slot sizes (misaligned
+    output offsets), stored runs, long runs (clipped chunks), one unit beyond the tile (handled by inflate_lz_kernel)."""
+    import random
+    from helpers import make_data
+    rng = random.Random(4242)
+    datas, streams, caps, wbs = [], [], [], []
+    for kind, n, lvl, wb in [(0, 65536, 6, 15), (1, 65536, 6, 15), (2, 65536, 6, 31), (3, 65535, 9, 31), (4, 60001, 6, 15),
+                             (0, 65536, 1, -15), (4, 65536, 0, 15), (0, 70000, 6, 15), (1, 33333, 6, 31), (0, 3, 6, 15)]:
+        d = make_data(rng, kind, n, alice)
+        datas.append(d)
+        streams.append(zcomp(d, lvl, wb))
+        caps.append(len(d))
+        wbs.append(wb)
+    for wbits in (15, 31, -15):
+        idx = [i for i in range(len(datas)) if wbs[i] == wbits]
+        ss = [streams[i] for i in idx]
+        cc = [caps[i] for i in idx]
+        ref_outs, ref_st, _ = oracle_inflate(ss, cc, wbits)
+        outs, st, ol, cons, _ = simlib.sim_inflate(ss, cc, wbits, D=-4, seed=7 + wbits)
+        assert_inflate_parity(outs, st, ref_outs, ref_st, "cta wbits %d" % wbits)
+        assert list(st) == [2] * len(idx)

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--kind", type=int, default=0)
     ap.add_argument("--cfgs", default="1,8;2,8;4,7;8,7;16,3;32,1")
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--lz", default="", help="phase B variants to time with the default kernel: 'cta_mode,spin_ns;...'")
     args = ap.parse_args()
     import torch
     from compu_b200 import _lib
@@ -53,9 +54,13 @@ def main():
     ws_bytes = int(L.cz_inflate_workspace_bytes(n, U))
     d_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     print(json.dumps({"streams": n, "kind": args.kind, "ratio": U / C, "host_compress_s": t_comp, "cores": os.cpu_count()}))
-    for cfg in args.cfgs.split(";"):
+    runs = [(cfg, None) for cfg in args.cfgs.split(";") if cfg] + [("-2,14", lz) for lz in args.lz.split(";") if lz]
+    for cfg, lz in runs:
         D, W = [int(x) for x in cfg.split(",")]
         L.cz_tune_inflate(D, W)
+        if lz:
+            L.cz_tune_inflate_lz(*[int(x) for x in lz.split(",")])
+            cfg = cfg + " lz " + lz
 
         def step():
             rc = L.cz_inflate_batch_device(sp, n, d_in.data_ptr(), d_in_off.data_ptr(), d_out.data_ptr(), d_out_off.data_ptr(),
