@@ -104,6 +104,8 @@ struct BitReader {
     uint32_t widx, wend;    // words merged into buf so far / number of words that hold stream bytes
     uint32_t cnt;           // valid bits in buf
     uint32_t nextw;         // words[widx], already loaded (0 past the end)
+    uint32_t nextw2;        // words[widx + 1], already loaded: a refill consumes a word that was requested two refills ago, so
+                            // two refills in a row (length code + distance code) do not wait for the memory round trip
     uint64_t buf;
     uint64_t total;         // bits in the unit
 
@@ -116,6 +118,7 @@ struct BitReader {
         cnt = 32 - sh;
         widx = wi + 1;
         nextw = load(widx);
+        nextw2 = load(widx + 1);
     }
     __device__ __forceinline__ void init(const uint8_t *p, uint64_t len) {
         mis = (uint32_t)((uintptr_t)p & 3);
@@ -130,7 +133,8 @@ struct BitReader {
             buf |= (uint64_t)nextw << cnt;
             cnt += 32;
             widx++;
-            nextw = load(widx);
+            nextw = nextw2;
+            nextw2 = load(widx + 1);
         }
     }
     __device__ __forceinline__ uint32_t peek(uint32_t n) const { return (uint32_t)buf & ((1u << n) - 1u); }
@@ -444,7 +448,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
 
     // ---- per-slot registers (meaningful on lanes < D)
     BitReader br;
-    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.total = 0;
+    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.nextw2 = 0; br.total = 0;
     int st = lane < D ? SS_IDLE : SS_EXIT;
     uint32_t unit = 0;
     const uint8_t *in_base = nullptr;

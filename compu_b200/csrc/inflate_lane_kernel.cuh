@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lane_kernel(InflateParams 
     __syncthreads();
 
     BitReader br;
-    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.total = 0;
+    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.nextw2 = 0; br.total = 0;
     int st = SS_IDLE;
     uint32_t unit = 0;
     const uint8_t *in_base = nullptr;

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lc_kernel(InflateParams P)
     __syncthreads();
 
     BitReader br;
-    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.total = 0;
+    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.nextw2 = 0; br.total = 0;
     uint32_t llim[8], dlim[8];
     lc_limits_reset(llim); lc_limits_reset(dlim);
     int st = SS_IDLE;

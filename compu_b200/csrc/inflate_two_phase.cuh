@@ -66,12 +66,16 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
     uint16_t *len_info = (uint16_t *)smem_raw;
     uint32_t *wscr = (uint32_t *)(smem_raw + 128) + warp * 64;
     LcSlot *slots = (LcSlot *)(smem_raw + 128 + WARPS * 256) + (size_t)warp * 32;
-    LcSlot &my = slots[lane];
+    uint32_t my_off = lane * (uint32_t)sizeof(LcSlot);
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+r"(my_off));  // keep the slot address in a register (otherwise it is recomputed from %tid per symbol)
+#endif
+    LcSlot &my = *(LcSlot *)((uint8_t *)slots + my_off);
     if (threadIdx.x < 32) len_info[threadIdx.x] = (uint16_t)(threadIdx.x < 29 ? lc_len_info(threadIdx.x) : 0);
     __syncthreads();
 
     BitReader br;
-    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.total = 0;
+    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.nextw2 = 0; br.total = 0;
     uint32_t llim[8], dlim[8];
     lc_limits_reset(llim); lc_limits_reset(dlim);
     int st = SS_IDLE;

@@ -297,6 +297,10 @@ inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b)
 }
 template <class T>
 inline T __ldg(const T *p) { return *p; }
+template <typename T>
+inline T __ldcs(const T *p) { return *p; }
+template <typename T, typename U>
+inline void __stcs(T *p, U v) { *p = (T)v; }
 inline unsigned __vcmpeq4(unsigned a, unsigned b) {
     unsigned r = 0;
     for (int i = 0; i < 4; i++)
