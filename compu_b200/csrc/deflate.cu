@@ -100,7 +100,13 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
         unsigned grid = nseg < (unsigned)ctx->sm_count * 12u ? nseg : (unsigned)ctx->sm_count * 12u;
         czk::deflate_chain_kernel<<<grid, 32, 0, st>>>(P);
     }
-    if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || !getenv("CZ_MATCH_TILED")) {
+    // CZ_MATCH_V=2: the candidate-pairs experiment (measured 92 ms vs 77 ms per GiB: it gives up find_match's pruning of
+    // candidates that cannot beat the best so far); CZ_MATCH_TILED=1: the tiled experiment; default: thread per position
+    static int match_v = -1;
+    if (match_v < 0) { const char *e = getenv("CZ_MATCH_V"); match_v = e ? atoi(e) : 1; }
+    if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && match_v == 2 && !getenv("CZ_MATCH_TILED")) {
+        czk::deflate_match_pairs_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
+    } else if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || !getenv("CZ_MATCH_TILED")) {
         czk::deflate_match_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
     } else {
         static bool configured[64] = {};

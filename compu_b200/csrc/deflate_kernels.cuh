@@ -234,6 +234,121 @@ __global__ void __launch_bounds__(256) deflate_match_kernel(DeflateParams P, uin
     P.match[g] = P.tune.level0 ? 0u : find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune);
 }
 
+// ------------------------------------------------------------------ K2 (candidate pairs; experiment, CZ_MATCH_V=2)
+// (Measured on B200: 92 ms per GiB against 77 ms for the simple kernel — every candidate is extended, while find_match()
+// skips the ones that cannot beat the best so far — so it is off by default.)
+// The same search as find_match(), split where the divergence is (profiles/r1_deflate_match_v2_ncu.md: with one thread
+// walking AND comparing, 12 of 32 lanes are active — chains differ in length, matches differ in length):
+//   walk     lane = position: follow the chain for up to CZK_MP_BATCH links and only RECORD the candidate distances
+//            (one dependent 2-byte load per link, nothing else);
+//   compare  the (position, candidate) pairs of the whole warp are compacted into one list and every lane takes a pair:
+//            first word, then word-wise extension — all 32 lanes busy whatever the chain lengths were;
+//   reduce   lane = position again: scan its candidates in chain order with find_match()'s rules (strictly longer wins,
+//            stop at nice_len / max_len), carry (best_len, best_dist) into the next batch of links.
+// The first batch is 2 links, so a position inside a long run stops after one 258-byte compare instead of 16.
+// Results are identical to find_match() (the quick rejects there never drop a candidate that would win).
+#define CZK_MP_BATCH 16u
+#define CZK_MP_STRIDE 17u  // u16 slots per lane (odd: lanes start in different banks)
+__global__ void __launch_bounds__(256) deflate_match_pairs_kernel(DeflateParams P, uint64_t total_bytes) {
+    __shared__ uint32_t s_seg;
+    __shared__ uint16_t s_cand[8][32 * CZK_MP_STRIDE];
+    __shared__ uint32_t s_pair[8][32 * CZK_MP_BATCH];
+    __shared__ uint16_t s_ml[8][32];
+    const uint64_t g0 = (uint64_t)blockIdx.x * 256;
+    if (threadIdx.x == 0) {
+        uint32_t lo = 0, hi = P.nseg;  // last segment with base <= g0
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (seg_base(P, mid) <= g0) lo = mid; else hi = mid;
+        }
+        s_seg = lo;
+    }
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t g = g0 + threadIdx.x;
+    const bool in_range = g < total_bytes;
+    uint32_t seg = s_seg;
+    if (in_range) while (seg + 1 < P.nseg && seg_base(P, seg + 1) <= g) seg++;
+    const uint64_t base = seg_base(P, seg);
+    const uint32_t pos = in_range ? (uint32_t)(g - base) : 0u;
+    const uint32_t n = in_range ? seg_len(P, seg) : 0u;
+    const uint8_t *gin = P.in + P.seg_off[0];   // byte g of the launch (segments are contiguous)
+    const uint16_t *pd = P.prevd + base;
+    uint32_t max_len = 0;
+    if (in_range && pos + CZK_MIN_MATCH <= n) { max_len = n - pos; if (max_len > CZK_MAX_MATCH) max_len = CZK_MAX_MATCH; }
+    bool active = max_len >= 4;
+    uint32_t total = 0, d = active ? pd[pos] : 0u, chain = P.tune.max_chain;
+    uint32_t best_len = 0, best_dist = 0;
+    const uint32_t nice = P.tune.nice_len;
+    uint16_t *cand = s_cand[warp] + lane * CZK_MP_STRIDE;
+    uint32_t *pair = s_pair[warp];
+    s_ml[warp][lane] = (uint16_t)max_len;
+    const uint64_t gw = g0 + warp * 32;  // byte index of lane 0's position
+    uint32_t batch = 2;
+    while (__any_sync(CZK_FULL, active)) {
+        // ---- walk
+        uint32_t cnt = 0;
+        for (uint32_t k = 0; k < batch; k++) {
+            if (active) {
+                if (d && chain) {
+                    chain--;
+                    total += d;
+                    if (total > CZK_WINDOW || total > pos) active = false;
+                    else {
+                        cand[cnt++] = (uint16_t)total;
+                        d = pd[pos - total];
+                    }
+                } else active = false;
+            }
+        }
+        // ---- compact the pairs of the warp
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t v = __shfl_up_sync(CZK_FULL, incl, sft);
+            if ((int)lane >= sft) incl += v;
+        }
+        const uint32_t npairs = __shfl_sync(CZK_FULL, incl, 31);
+        const uint32_t off = incl - cnt;
+        for (uint32_t k = 0; k < cnt; k++) pair[off + k] = (uint32_t)cand[k] | (lane << 25);
+        __syncwarp();
+        // ---- compare: one pair per lane
+        for (uint32_t j = lane; j < npairs; j += 32) {
+            const uint32_t e = pair[j];
+            const uint32_t owner = e >> 25, tot = e & 0xffffu;
+            const uint32_t ml = s_ml[warp][owner];
+            const uint8_t *cur = gin + gw + owner;
+            const uint8_t *cd = cur - tot;
+            uint32_t l = 0;
+            if (load32u(cd) == load32u(cur)) {
+                l = 4;
+                while (l + 4 <= ml) {
+                    const uint32_t x = load32u(cd + l) ^ load32u(cur + l);
+                    if (x) { l += ctz32(x) >> 3; break; }
+                    l += 4;
+                }
+                if (l + 4 > ml)
+                    while (l < ml && cd[l] == cur[l]) l++;
+            }
+            pair[j] = e | (l << 16);
+        }
+        __syncwarp();
+        // ---- reduce in chain order
+        for (uint32_t k = 0; k < cnt; k++) {
+            const uint32_t e = pair[off + k];
+            const uint32_t l = (e >> 16) & 0x1ffu;
+            if (l > best_len) {
+                best_len = l;
+                best_dist = e & 0xffffu;
+                if (l >= nice || l == max_len) { active = false; break; }
+            }
+        }
+        __syncwarp();
+        batch = CZK_MP_BATCH;
+    }
+    if (in_range) P.match[g] = best_len >= CZK_MIN_MATCH ? (best_len | (best_dist << 9)) : 0u;
+}
+
 // ------------------------------------------------------------------ K2 (tiled)
 // The same search as find_match(), restructured for the machine (profiles/r1_deflate_match_v2_ncu.md: the simple
 // thread-per-position kernel runs with 12 of 32 lanes active and waits on L1/L2 for every link of the chain):

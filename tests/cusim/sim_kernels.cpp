@@ -91,7 +91,9 @@ extern "C" int sim_deflate(size_t nseg, size_t n_units, const uint8_t *in, const
     const unsigned ns = P.nseg, nu = P.n_units, nsl = P.n_slots;
     if (P.check_kind) cusim::launch(ns < 3 ? ns : 3, 128, 0, deflate_checksum_kernel, P);
     if (!P.tune.level0 && !P.tune.huffman_only && !P.tune.rle_only) cusim::launch(ns < 3 ? ns : 3, 32, 0, deflate_chain_kernel, P);
-    if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || (seed & 2))
+    if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && (seed % 3) == 0)
+        cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_match_pairs_kernel, P, in_bytes);
+    else if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || (seed & 2))
         cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_match_kernel, P, in_bytes);
     else
         cusim::launch((unsigned)((in_bytes >> 12) + nseg + 1), CZK_MT_THREADS, deflate_match_tiled_smem(), deflate_match_tiled_kernel, P);

@@ -54,13 +54,14 @@ def test_sim_deflate_roundtrip_containers(alice, wbits):
         assert streams[0][:10] == bytes([0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 3])
 
 
-def test_sim_deflate_matches_sequential_model(alice):
+@pytest.mark.parametrize("seed", [1, 2, 3])  # 1: tiled match kernel, 2: thread-per-position, 3: candidate pairs
+def test_sim_deflate_matches_sequential_model(alice, seed):
     L = model_lib()
     rng = random.Random(11)
     # the 230 000-byte unit crosses the 64 KiB wrap of the 16-bit head table and several sweeps
     units = [make_data(rng, k, n, alice) for k, n in [(0, 40000), (1, 3000), (2, 5000), (3, 9000), (4, 20000), (0, 17)]]
     units.append((alice + alice[:80000])[:230000])
-    streams, st, lens, _, seg_sizes = simlib.sim_deflate(units, seg_bytes=1 << 20, window_bits=-15, piece_mode=1)
+    streams, st, lens, _, seg_sizes = simlib.sim_deflate(units, seg_bytes=1 << 20, window_bits=-15, piece_mode=1, seed=seed)
     assert list(st) == [2] * len(units)
     for u, s in zip(units, streams):
         assert s == model_segment(L, u), "kernel chain differs from the sequential run of the same decisions"
@@ -75,6 +76,10 @@ def test_sim_deflate_levels_and_strategies(alice, level, strategy):
     assert list(st) == [2] * len(units)
     for u, s in zip(units, streams):
         assert dec(s, 15) == u
+    # every match kernel makes the same decisions: identical bytes
+    for seed in (2, 3):
+        streams2, st2, _, _, _ = simlib.sim_deflate(units, seg_bytes=16384, level=level, strategy=strategy, window_bits=15, seed=seed)
+        assert streams2 == streams and list(st2) == list(st)
 
 
 def test_sim_deflate_packed_and_capacity(alice):
