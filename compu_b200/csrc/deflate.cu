@@ -37,7 +37,7 @@ static inline uint64_t segment_bound(uint64_t len) { return len + len / 2048 + 6
 
 // ---- workspace carving (device) ---------------------------------------------------------------------------------
 struct WsLayout {
-    uint64_t st, prevd, match, blk_end, freqs, plans, pos, total, n_slots, bytes;
+    uint64_t st, prevd, prevd2, match, blk_end, freqs, plans, pos, total, n_slots, bytes;
 };
 static WsLayout ws_layout(uint64_t nseg, uint64_t n_units, uint64_t in_bytes) {
     WsLayout w;
@@ -45,6 +45,7 @@ static WsLayout ws_layout(uint64_t nseg, uint64_t n_units, uint64_t in_bytes) {
     uint64_t o = 0;
     w.st = o; o = align_up(o + nseg * sizeof(SegState), 256);
     w.prevd = o; o = align_up(o + 2 * (in_bytes + 8), 256);
+    w.prevd2 = o; o = align_up(o + 2 * (in_bytes + 8), 256);
     w.match = o; o = align_up(o + 4 * (in_bytes + 8), 256);
     w.blk_end = o; o = align_up(o + 4 * w.n_slots, 256);
     w.freqs = o; o = align_up(o + 4ull * CZK_FREQ_STRIDE * w.n_slots, 256);
@@ -86,7 +87,7 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
     P.total_out = L.packed ? (uint64_t *)(ws + w.total) : nullptr;
     P.unit_out_len = L.d_unit_out_len; P.unit_status = L.d_unit_status; P.unit_checks = L.d_unit_checks;
     P.seg_out_bytes = L.d_seg_out_bytes;
-    P.st = (SegState *)(ws + w.st); P.prevd = (uint16_t *)(ws + w.prevd); P.match = (uint32_t *)(ws + w.match);
+    P.st = (SegState *)(ws + w.st); P.prevd = (uint16_t *)(ws + w.prevd); P.prevd2 = (uint16_t *)(ws + w.prevd2); P.match = (uint32_t *)(ws + w.match);
     P.blk_end = (uint32_t *)(ws + w.blk_end); P.freqs = (uint32_t *)(ws + w.freqs); P.plans = (BlockPlan *)(ws + w.plans);
     P.crc = ctx->d_crc;
     P.tune = czk::deflate_tuning(L.level, L.strategy);
@@ -99,7 +100,13 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
     if (!P.tune.level0 && !P.tune.huffman_only && !P.tune.rle_only) {
         unsigned grid = nseg < (unsigned)ctx->sm_count * 12u ? nseg : (unsigned)ctx->sm_count * 12u;
         czk::deflate_chain_kernel<<<grid, 32, 0, st>>>(P);
-    }
+        // CZ_MATCH_LINKS=2: build the second-link array and fetch two candidates per step (measured 124.5 ms per GiB against
+        // 110.4 ms for the single-link walk: the speculative loads of the second candidate cost more than the round trip saved)
+        static int two_links = -1;
+        if (two_links < 0) { const char *e = getenv("CZ_MATCH_LINKS"); two_links = e ? atoi(e) == 2 : 0; }
+        if (two_links) czk::deflate_chain2_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
+        else P.prevd2 = nullptr;
+    } else P.prevd2 = nullptr;
     // CZ_MATCH_V=2: the candidate-pairs experiment (measured 92 ms vs 77 ms per GiB: it gives up find_match's pruning of
     // candidates that cannot beat the best so far); CZ_MATCH_TILED=1: the tiled experiment; default: thread per position
     static int match_v = -1;

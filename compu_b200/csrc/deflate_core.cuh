@@ -85,18 +85,64 @@ __host__ __device__ inline uint32_t hash4(uint32_t v) { return (v * 2654435761u)
 #ifdef CZK_COUNT_STEPS
 static unsigned long long czk_step_count = 0;
 #endif
+// State of one find_match() call (the current position's first 16 bytes stay in registers: most matches end inside them).
+struct MatchScan {
+    const uint8_t *cur;
+    uint32_t max_len, cur4, curw1, curw2, curw3;
+    uint32_t best_len, best_dist, cur_end;  // cur_end = cur[best_len] once there is a match (best_len < max_len then)
+};
+
+// Examine one candidate `total` bytes back, whose first word (c4) and byte at best_len (cb) are already loaded.
+// Returns true when the search is over (nice length or the longest possible match).
+__host__ __device__ inline bool match_try(MatchScan &m, uint32_t total, uint32_t c4, uint32_t cb, const DeflateTuning &t, uint32_t &chain) {
+    // quick rejects (zlib's order): the byte that would extend the best match, then the first word
+    if (!((m.best_len < 4 || cb == m.cur_end) && c4 == m.cur4)) return false;
+    const uint8_t *cand = m.cur - total;
+    const uint32_t max_len = m.max_len;
+    uint32_t l = 4;
+    bool open = true;  // no mismatch found yet
+#define CZK_FM_STEP(cw)                                               \
+    if (open && l + 4 <= max_len) {                                   \
+        const uint32_t x = load32u(cand + l) ^ (cw);                  \
+        if (x) { l += ctz32(x) >> 3; open = false; } else l += 4;     \
+    }
+    CZK_FM_STEP(m.curw1) CZK_FM_STEP(m.curw2) CZK_FM_STEP(m.curw3)
+#undef CZK_FM_STEP
+    if (open) {
+        while (l + 4 <= max_len) {
+            const uint32_t x = load32u(cand + l) ^ load32u(m.cur + l);
+            if (x) { l += ctz32(x) >> 3; break; }
+            l += 4;
+        }
+    }
+    if (l + 4 > max_len)  // fewer than 4 bytes left to compare (or ran to the end): finish byte-wise
+        while (l < max_len && cand[l] == m.cur[l]) l++;
+    if (l > m.best_len) {
+        m.best_len = l;
+        m.best_dist = total;
+        if (l >= t.nice_len || l == max_len) return true;
+        m.cur_end = m.cur[l];
+#ifdef CZK_GOOD_LEN  // experiment (tests/model sweeps): zlib's good_length rule
+        if (l >= CZK_GOOD_LEN) chain >>= 2;
+#endif
+    }
+    return false;
+}
+
 // Best match for position `pos` of a segment: walk the chain of earlier positions with the same 4-byte hash
 // (prevd[i] = distance from i to the previous such position, 0 = none), newest first. Returns len | dist << 9, or 0.
 // Matches never cross the end of the segment and never look farther back than the segment start. A candidate must agree
 // on the first 4 bytes (the hash is over 4 bytes, so the chain holds little else); comparison is word-wise.
+// prevd2 (optional): prevd2[i] = distance from i to the SECOND previous position of its chain (0 = none or beyond the
+// window). The walk is a chain of dependent loads; with the second link a step fetches two candidates and the links of the
+// node after them in one memory round trip. Same candidates, same order, same result as the single-link walk.
 __host__ __device__ inline uint32_t find_match(const uint8_t *seg, uint32_t seg_len, const uint16_t *prevd, uint32_t pos,
-                                               const DeflateTuning &t) {
+                                               const DeflateTuning &t, const uint16_t *prevd2 = nullptr) {
     if (pos + CZK_MIN_MATCH > seg_len) return 0;
     uint32_t max_len = seg_len - pos;
     if (max_len > CZK_MAX_MATCH) max_len = CZK_MAX_MATCH;
     if (t.huffman_only) return 0;
     const uint8_t *cur = seg + pos;
-    uint32_t best_len = 0, best_dist = 0;
     if (t.rle_only) {
         if (pos == 0) return 0;
         uint32_t l = 0;
@@ -104,36 +150,66 @@ __host__ __device__ inline uint32_t find_match(const uint8_t *seg, uint32_t seg_
         return l >= CZK_MIN_MATCH ? (l | (1u << 9)) : 0;
     }
     if (max_len < 4) return 0;  // the chains are built from 4-byte hashes: the last 3 positions have no link
-    const uint32_t cur4 = load32u(cur);
-    uint32_t total = 0, d = prevd[pos], chain = t.max_chain;
-    while (d && chain--) {
+    MatchScan m;
+    m.cur = cur; m.max_len = max_len;
+    m.cur4 = load32u(cur);
+    m.curw1 = max_len >= 8 ? load32u(cur + 4) : 0u;
+    m.curw2 = max_len >= 12 ? load32u(cur + 8) : 0u;
+    m.curw3 = max_len >= 16 ? load32u(cur + 12) : 0u;
+    m.best_len = 0; m.best_dist = 0; m.cur_end = 0;
+    uint32_t total = 0, chain = t.max_chain;
+    if (prevd2) {
+        uint32_t d1 = prevd[pos], d2 = prevd2[pos];
+        while (d1 && chain) {
+            const uint32_t ta = total + d1;
+            if (ta > CZK_WINDOW || ta > pos) break;
+            const uint32_t tb = total + d2;
+            const bool hasb = d2 != 0 && tb <= CZK_WINDOW && tb <= pos;  // (d2 > d1 whenever it is not 0)
+            // everything this step needs is requested before anything is used
+            const uint32_t c4a = load32u(cur - ta);
+            const uint32_t cba = m.best_len >= 4 ? *(cur - ta + m.best_len) : 0u;
+            uint32_t c4b = 0, cbb = 0, n1 = 0, n2 = 0;
+            if (hasb) {
+                c4b = load32u(cur - tb);
+                cbb = m.best_len >= 4 ? *(cur - tb + m.best_len) : 0u;
+                n1 = prevd[pos - tb];
+                n2 = prevd2[pos - tb];
+            }
 #ifdef CZK_COUNT_STEPS
-        czk_step_count++;
+            czk_step_count++;
 #endif
-        total += d;
-        if (total > CZK_WINDOW || total > pos) break;
-        const uint8_t *cand = cur - total;
-        // quick rejects: the first word, then the word that ends at the byte which would extend the best match
-        if (load32u(cand) == cur4 && (best_len < 4 || best_len >= max_len || load32u(cand + best_len - 3) == load32u(cur + best_len - 3))) {
-            uint32_t l = 4;
-            while (l + 4 <= max_len) {
-                const uint32_t x = load32u(cand + l) ^ load32u(cur + l);
-                if (x) { l += ctz32(x) >> 3; break; }
-                l += 4;
-            }
-            if (l + 4 > max_len)  // fewer than 4 bytes left to compare (or ran to the end): finish byte-wise
-                while (l < max_len && cand[l] == cur[l]) l++;
-            if (l > best_len) {
-                best_len = l;
-                best_dist = total;
-                if (l >= t.nice_len || l == max_len) break;
-#ifdef CZK_GOOD_LEN  // experiment (tests/model sweeps): zlib's good_length rule
-                if (l >= CZK_GOOD_LEN) chain >>= 2;
+            chain--;
+            const uint32_t bl0 = m.best_len;
+            if (match_try(m, ta, c4a, cba, t, chain)) break;
+            if (!hasb || !chain) break;  // the chain ends after the first candidate (no further link / budget used up)
+#ifdef CZK_COUNT_STEPS
+            czk_step_count++;
 #endif
-            }
+            chain--;
+            if (m.best_len != bl0) cbb = *(cur - tb + m.best_len);  // the first candidate moved the goal
+            if (match_try(m, tb, c4b, cbb, t, chain)) break;
+            total = tb;
+            d1 = n1;
+            d2 = n2;
         }
-        d = prevd[pos - total];
+    } else {
+        uint32_t d = prevd[pos];
+        while (d && chain--) {
+#ifdef CZK_COUNT_STEPS
+            czk_step_count++;
+#endif
+            total += d;
+            if (total > CZK_WINDOW || total > pos) break;
+            // the next link, the candidate's first word and the byte that would extend the best match are requested together:
+            // the walk is a chain of dependent loads, and this way one step costs one memory round trip instead of three
+            const uint32_t dnext = prevd[pos - total];
+            const uint32_t c4 = load32u(cur - total);
+            const uint32_t cb = m.best_len >= 4 ? *(cur - total + m.best_len) : 0u;
+            if (match_try(m, total, c4, cb, t, chain)) break;
+            d = dnext;
+        }
     }
+    const uint32_t best_len = m.best_len, best_dist = m.best_dist;
     if (best_len < CZK_MIN_MATCH) return 0;
     return best_len | (best_dist << 9);
 }

@@ -61,6 +61,7 @@ struct DeflateParams {
     uint64_t *total_out;           // packed mode: total bytes written (1 value)
     SegState *st;                  // nseg
     uint16_t *prevd;
+    uint16_t *prevd2;              // second link of every position (K1b), or null
     uint32_t *match;
     uint32_t *blk_end;             // n_slots
     uint32_t *freqs;               // n_slots * CZK_FREQ_STRIDE
@@ -211,6 +212,37 @@ __global__ void __launch_bounds__(32) deflate_chain_kernel(DeflateParams P) {
     }
 }
 
+// ------------------------------------------------------------------ K1b
+// Second link of every chain node: prevd2[i] = prevd[i] + prevd[i - prevd[i]] (0 = none, or farther than the window).
+// With it the match search fetches two candidates per memory round trip (find_match).
+__global__ void __launch_bounds__(256) deflate_chain2_kernel(DeflateParams P, uint64_t total_bytes) {
+    __shared__ uint32_t s_seg;
+    const uint64_t g0 = (uint64_t)blockIdx.x * 256;
+    if (threadIdx.x == 0) {
+        uint32_t lo = 0, hi = P.nseg;  // last segment with base <= g0
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (seg_base(P, mid) <= g0) lo = mid; else hi = mid;
+        }
+        s_seg = lo;
+    }
+    __syncthreads();
+    const uint64_t g = g0 + threadIdx.x;
+    if (g >= total_bytes) return;
+    uint32_t seg = s_seg;
+    while (seg + 1 < P.nseg && seg_base(P, seg + 1) <= g) seg++;
+    const uint64_t base = seg_base(P, seg);
+    const uint32_t pos = (uint32_t)(g - base);
+    const uint16_t *pd = P.prevd + base;
+    const uint32_t d1 = pd[pos];
+    uint32_t d2 = 0;
+    if (d1 && d1 <= pos) {
+        const uint32_t dd = pd[pos - d1];
+        if (dd && d1 + dd <= CZK_WINDOW) d2 = d1 + dd;
+    }
+    P.prevd2[g] = (uint16_t)d2;
+}
+
 // ------------------------------------------------------------------ K2
 // 256 consecutive input bytes per CTA; a tile may straddle segment boundaries.
 __global__ void __launch_bounds__(256) deflate_match_kernel(DeflateParams P, uint64_t total_bytes) {
@@ -231,7 +263,7 @@ __global__ void __launch_bounds__(256) deflate_match_kernel(DeflateParams P, uin
     while (seg + 1 < P.nseg && seg_base(P, seg + 1) <= g) seg++;
     const uint64_t base = seg_base(P, seg);
     const uint32_t pos = (uint32_t)(g - base);
-    P.match[g] = P.tune.level0 ? 0u : find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune);
+    P.match[g] = P.tune.level0 ? 0u : find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, P.prevd2 ? P.prevd2 + base : nullptr);
 }
 
 // ------------------------------------------------------------------ K2 (candidate pairs; experiment, CZ_MATCH_V=2)

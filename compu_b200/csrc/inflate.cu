@@ -112,7 +112,7 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
     // phase B of units whose output slot fits the shared-memory tile runs one CTA per unit (CZ_LZ_CTA=0: off)
     if (g_lz_cta < 0) { const char *e = getenv("CZ_LZ_CTA"); g_lz_cta = e ? atoi(e) : 0; }
     if (g_lz_spin < 0) { const char *e = getenv("CZ_LZ_SPIN_NS"); g_lz_spin = e ? atoi(e) : 100; }
-    Q.cta_tile = g_lz_cta ? CZK_LZ_TILE : 0;
+    Q.cta_tile = (g_lz_cta == 1 || g_lz_cta == 2) ? CZK_LZ_TILE : 0;
     Q.spin_ns = (uint32_t)g_lz_spin;
     constexpr int WC = 8;
     auto kc = czk::inflate_lz_cta_kernel<WC, 32 / WC>;
@@ -169,6 +169,18 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
     if (lz_cap < 0) { const char *e = getenv("CZ_LZ_CTAS_PER_SM"); lz_cap = e ? atoi(e) : 0; }
     gmax = (uint64_t)ctx->sm_count * (lz_cap > 0 && lz_cap < per_sm_b[d] ? lz_cap : per_sm_b[d]);
     if (gb > gmax) gb = gmax;
+    // phase B variants with several tokens per lane (cz_tune_inflate_lz / CZ_LZ_CTA = 3..7)
+#define CZ_LZW(mode, TPL, SHORT, MINB)                                                                              \
+    if (g_lz_cta == mode) {                                                                                         \
+        auto kw = czk::inflate_lzw_kernel<8, TPL, SHORT, MINB>;                                                     \
+        static int per_sm_w[64] = {};                                                                               \
+        if (!per_sm_w[d] && !CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_w[d], kw, 256, 0))) return CZ_E_MEM; \
+        uint64_t gw = (P.n + 7) / 8, gwmax = (uint64_t)ctx->sm_count * (per_sm_w[d] > MINB ? MINB : per_sm_w[d]);  \
+        if (gw > gwmax) gw = gwmax;                                                                                 \
+        kw<<<(unsigned)gw, 256, 0, st>>>(Q);                                                                        \
+    } else
+    CZ_LZW(3, 2, 12, 3) CZ_LZW(4, 2, 12, 2) CZ_LZW(5, 4, 8, 2) CZ_LZW(6, 2, 8, 4) CZ_LZW(7, 4, 8, 3)
+#undef CZ_LZW
     kb<<<(unsigned)gb, WB * 32, 0, st>>>(Q);
     if (g_prof_on) {
         cudaEventRecord(pr.e2, st);

@@ -55,6 +55,9 @@ __host__ __device__ inline uint64_t tok_word_off(uint64_t out_off, uint64_t unit
 #define CZK_TOK_LIT 0x80000000u
 #define CZK_TOK_STORED 0xC0000000u
 #define CZK_TOK_TAIL 0x20000000u
+#ifndef CZK_LZ_MINB
+#define CZK_LZ_MINB 1
+#endif
 #define CZK_LZ_SHORT 12  // phase B (token-parallel): matches up to this long are copied by their own lane (8/12/16/24/32 measured: 33.9/32.6/34.0/35.5/38.0 ms)
 
 template <int WARPS>
@@ -319,7 +322,7 @@ constexpr size_t inflate_tok_smem_bytes() { return 128 + WARPS * 256 + sizeof(Lc
 // ---------------------------------------------------------------------------------------------------------------
 // Phase B: one warp per unit.
 template <int WARPS, int H>
-__global__ void __launch_bounds__(WARPS * 32) inflate_lz_kernel(TwoPhaseParams Q) {
+__global__ void __launch_bounds__(WARPS * 32, CZK_LZ_MINB) inflate_lz_kernel(TwoPhaseParams Q) {
     const InflateParams &P = Q.base;
     __shared__ uint32_t crc_tab[256 + 34];
     const uint32_t lane = threadIdx.x & 31;
@@ -515,6 +518,201 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lz_kernel(TwoPhaseParams Q
                 ti += 3;
             }
             // ---- checksums over freshly written output (L1/L2 hits), in pieces
+            if ((want_adler || want_crc) && (opos - ck_pos >= 8192 || ti >= ntok)) {
+                uint64_t to = opos;
+                if (ti < ntok) to = ck_pos + ((to - ck_pos) & ~(uint64_t)127);  // keep CRC pieces at 128 B until the end
+                if (want_adler) {
+                    for (uint64_t p = ck_pos; p < to; p += 8192) {
+                        uint32_t n = (uint32_t)(to - p < 8192 ? to - p : 8192);
+                        adler = warp_adler32(adler, ob + p, n, lane);
+                    }
+                }
+                if (want_crc) {
+                    uint64_t p = ck_pos;
+                    while (to - p >= 128) {
+                        uint32_t q = (uint32_t)((to - p) >> 7);
+                        if (q > 32) q = 32;
+                        crc = warp_crc32_pieces(crc, ob + p, q, crc_tab, crc_pow, lane);
+                        p += (uint64_t)q * 128;
+                    }
+                    if (p < to) {
+                        uint32_t c2 = 0;
+                        if (lane == 0) c2 = crc32_serial(crc, ob + p, (uint32_t)(to - p), crc_tab);
+                        crc = __shfl_sync(CZK_FULL, c2, 0);
+                    }
+                }
+                ck_pos = to;
+            }
+        }
+        if (lane == 0) {
+            int status = m.status;
+            if (status == ST_FINISHED && !P.segment_mode) {
+                if (m.wrap == 1 && m.expect != adler) status = ST_E_DATA;  // "incorrect data check"
+                if (m.wrap == 2 && m.expect != crc) status = ST_E_DATA;
+            }
+            P.out_lens[unit] = opos;
+            P.statuses[unit] = status;
+            if (P.checks) { P.checks[2 * unit] = adler; P.checks[2 * unit + 1] = crc; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Phase B, one warp per unit, TPL tokens per lane (32 * TPL tokens per step). Same resolution rule as the token-parallel
+// branch of inflate_lz_kernel (a token is ready when the part of this step it reads lies below the first unfinished token),
+// but a step covers TPL times as many tokens: the token load and the scan are paid once per 32 * TPL tokens, the
+// back-reference loads of all ready tokens of the step are in flight together, and fewer warps (= fewer 32 KiB windows
+// competing for L2) keep the same number of loads in flight.
+template <int WARPS, int TPL, int SHORT, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) inflate_lzw_kernel(TwoPhaseParams Q) {
+    const InflateParams &P = Q.base;
+    __shared__ uint32_t crc_tab[256 + 34];
+    const uint32_t lane = threadIdx.x & 31;
+    if (P.crc)
+        for (uint32_t i = threadIdx.x; i < 256 + 34; i += WARPS * 32) crc_tab[i] = i < 256 ? P.crc->table[i] : P.crc->pow128[i - 256];
+    __syncthreads();
+    const uint32_t *crc_pow = crc_tab + 256;
+
+    for (;;) {
+        unsigned long long u64 = 0;
+        if (lane == 0) u64 = atomicAdd(Q.counter_b, 1ull);
+        u64 = __shfl_sync(CZK_FULL, u64, 0);
+        if (u64 >= P.n) break;
+        const uint32_t unit = P.ids ? P.ids[u64] : (uint32_t)u64;
+        const uint64_t o0 = P.out_off[unit];
+        if (Q.cta_tile && P.out_off[unit + 1] - o0 <= Q.cta_tile) continue;  // resolved by inflate_lz_cta_kernel
+        const TokMeta m = Q.meta[unit];
+        uint8_t *ob = P.out + o0;
+        const uint8_t *ib = P.in + P.in_off[unit];
+        const uint32_t *tok = Q.tok + tok_word_off(o0 - P.out_off[0], unit);
+        const uint32_t ntok = m.ntok;
+        const bool by_kind = P.segment_mode || (P.checks && m.wrap == 0);
+        const bool want_adler = by_kind ? (P.check_kind & 1) : m.wrap == 1;
+        const bool want_crc = by_kind ? (P.check_kind & 2) : m.wrap == 2;
+        uint64_t opos = 0, ck_pos = 0;
+        uint32_t adler = 1, crc = 0;
+        uint32_t ti = 0;
+        while (ti < ntok) {
+            uint32_t t[TPL];
+            uint32_t nt = 32u * TPL;
+            bool stop_found = false;
+#pragma unroll
+            for (int u = 0; u < TPL; u++) {
+                const uint32_t i = ti + 32u * u + lane;
+                t[u] = i < ntok ? tok[i] : CZK_TOK_STORED;  // past the end: acts as a stop mark
+            }
+#pragma unroll
+            for (int u = 0; u < TPL; u++) {
+                const uint32_t stopm = __ballot_sync(CZK_FULL, (t[u] >> 30) == 3u);
+                if (!stop_found && stopm) { nt = 32u * u + (uint32_t)__ffs((int)stopm) - 1u; stop_found = true; }
+            }
+            if (nt) {
+                uint32_t tl[TPL];
+                int ipos[TPL], dep_end[TPL];
+                bool done[TPL], coop[TPL];
+                uint32_t carry = 0;
+#pragma unroll
+                for (int u = 0; u < TPL; u++) {
+                    if (32u * u + lane >= nt) t[u] = 0u;
+                    tl[u] = (t[u] >> 31) ? ((t[u] >> 24) & 3u) : (t[u] & 0x1ffu);
+                    uint32_t pos = tl[u];
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t v = __shfl_up_sync(CZK_FULL, pos, d);
+                        if ((int)lane >= d) pos += v;
+                    }
+                    const uint32_t tot = __shfl_sync(CZK_FULL, pos, 31);
+                    ipos[u] = (int)(carry + pos - tl[u]);
+                    carry += tot;
+                    const bool is_tok = 32u * u + lane < nt;
+                    const bool is_match = is_tok && !(t[u] >> 31);
+                    const uint32_t dist = (t[u] >> 9) & 0xffffu;
+                    dep_end[u] = 0;
+                    if (is_match) { dep_end[u] = ipos[u] - (int)dist + (int)tl[u]; if (dep_end[u] > ipos[u]) dep_end[u] = ipos[u]; }
+                    coop[u] = is_match && (tl[u] > (uint32_t)SHORT || dist < tl[u]);
+                    done[u] = !is_tok;
+                }
+                const uint32_t total = carry;
+                uint8_t *obp = ob + opos;
+                for (;;) {
+                    int frontier = (int)total;
+                    bool any = false;
+#pragma unroll
+                    for (int u = 0; u < TPL; u++) {
+                        const uint32_t und = __ballot_sync(CZK_FULL, !done[u]);
+                        if (!any && und) { frontier = __shfl_sync(CZK_FULL, ipos[u], __ffs((int)und) - 1); any = true; }
+                    }
+                    if (!any) break;
+                    bool ready[TPL];
+                    uint32_t bb[TPL][SHORT];
+#pragma unroll
+                    for (int u = 0; u < TPL; u++) {
+                        ready[u] = !done[u] && dep_end[u] <= frontier;
+                        if (ready[u] && !coop[u] && !(t[u] >> 31)) {
+                            const uint8_t *sp = obp + ipos[u] - (int)((t[u] >> 9) & 0xffffu);
+#pragma unroll
+                            for (int k = 0; k < SHORT; k++) bb[u][k] = k < (int)tl[u] ? sp[k] : 0u;
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < TPL; u++) {
+                        if (ready[u] && !coop[u]) {
+                            uint8_t *d = obp + ipos[u];
+                            if (t[u] >> 31) {
+                                d[0] = (uint8_t)t[u];
+                                if (tl[u] > 1) d[1] = (uint8_t)(t[u] >> 8);
+                                if (tl[u] > 2) d[2] = (uint8_t)(t[u] >> 16);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < SHORT; k++) if (k < (int)tl[u]) d[k] = (uint8_t)bb[u][k];
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < TPL; u++) {
+                        uint32_t cm = __ballot_sync(CZK_FULL, ready[u] && coop[u]);
+                        while (cm) {
+                            const int sl = __ffs((int)cm) - 1;
+                            cm &= cm - 1;
+                            const uint32_t Ln = __shfl_sync(CZK_FULL, tl[u], sl), D = (__shfl_sync(CZK_FULL, t[u], sl) >> 9) & 0xffffu;
+                            const int P0 = __shfl_sync(CZK_FULL, ipos[u], sl);
+                            uint8_t *d = obp + P0;
+                            const uint8_t *sp = d - D;  // bytes [P0 - D, P0) are complete
+                            if (D >= Ln) {
+                                for (uint32_t k = lane; k < Ln; k += 32) d[k] = sp[k];
+                            } else if (D >= 32) {
+                                for (uint32_t k0 = 0; k0 < Ln; k0 += 32) {
+                                    const uint32_t k = k0 + lane;
+                                    if (k < Ln) d[k] = sp[k];
+                                    __syncwarp();
+                                }
+                            } else {
+                                uint32_t r = lane % D;
+                                const uint32_t stepD = 32u % D;
+                                for (uint32_t k = lane; k < Ln; k += 32) {
+                                    d[k] = sp[r];
+                                    r += stepD;
+                                    if (r >= D) r -= D;
+                                }
+                            }
+                        }
+                        done[u] = done[u] || ready[u];
+                    }
+                    __syncwarp();
+                }
+                opos += total;
+                ti += nt;
+            }
+            if (nt < 32u * TPL && ti < ntok) {
+                // a stored run: three marked words starting at ti
+                const uint32_t w0 = tok[ti], w1 = tok[ti + 1], w2 = tok[ti + 2];
+                const uint32_t n = w0 & 0xffffu;
+                const uint64_t ipos_in = (uint64_t)(w1 & 0x1fffffffu) | ((uint64_t)(w2 & 0x1fffffffu) << 29);
+                for (uint32_t k = lane; k < n; k += 32) ob[opos + k] = ib[ipos_in + k];
+                __syncwarp();
+                opos += n;
+                ti += 3;
+            }
             if ((want_adler || want_crc) && (opos - ck_pos >= 8192 || ti >= ntok)) {
                 uint64_t to = opos;
                 if (ti < ntok) to = ck_pos + ((to - ck_pos) & ~(uint64_t)127);  // keep CRC pieces at 128 B until the end

@@ -34,7 +34,9 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
         case -1: cusim::launch(grid, 2 * 32, inflate_lc_smem_bytes<2>(), inflate_lc_kernel<2>, P); break;
         case -2:
         case -3:
-        case -4: {
+        case -4:
+        case -5:
+        case -6: {
             const uint64_t total_out = out_off[n] - out_off[0];
             std::vector<uint32_t> tok(total_out + 8 * n + 64, 0xDEADBEEFu);
             std::vector<TokMeta> meta(n);
@@ -46,7 +48,9 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
             if (D == -4) {
                 cusim::launch(grid, 8 * 32, inflate_lz_cta_smem_bytes<8>(), inflate_lz_cta_kernel<8, 4>, Q);
                 cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 0>, Q);
-            } else if (D == -3) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 0>, Q);
+            } else if (D == -5) cusim::launch(grid, 2 * 32, 0, inflate_lzw_kernel<2, 2, 12, 1>, Q);
+            else if (D == -6) cusim::launch(grid, 2 * 32, 0, inflate_lzw_kernel<2, 4, 8, 1>, Q);
+            else if (D == -3) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 0>, Q);
             else if (seed % 3 == 0) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 4>, Q);
             else if (seed % 3 == 1) cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 2>, Q);
             else cusim::launch(grid, 2 * 32, 0, inflate_lz_kernel<2, 0>, Q);
@@ -75,7 +79,7 @@ extern "C" int sim_deflate(size_t nseg, size_t n_units, const uint8_t *in, const
     const uint64_t in_bytes = seg_off[nseg] - seg_off[0];
     const uint64_t n_slots = (in_bytes >> 14) + nseg + 1;
     std::vector<SegState> st(nseg);
-    std::vector<uint16_t> prevd(in_bytes + 8);
+    std::vector<uint16_t> prevd(in_bytes + 8), prevd2(in_bytes + 8);
     std::vector<uint32_t> match(in_bytes + 8), blk_end(n_slots), freqs(n_slots * CZK_FREQ_STRIDE);
     std::vector<BlockPlan> plans(n_slots);
     DeflateParams P;
@@ -83,14 +87,17 @@ extern "C" int sim_deflate(size_t nseg, size_t n_units, const uint8_t *in, const
     P.in = in; P.out = out; P.seg_off = seg_off; P.nseg = (uint32_t)nseg; P.n_units = (uint32_t)n_units; P.n_slots = (uint32_t)n_slots;
     P.unit_seg = unit_seg; P.unit_out_off = unit_out_off; P.unit_out_pos = packed ? unit_out_pos : nullptr;
     P.total_out = packed ? total_out : nullptr; P.unit_out_len = unit_out_len; P.unit_status = unit_status;
-    P.unit_checks = unit_checks; P.seg_out_bytes = seg_out_bytes; P.st = st.data(); P.prevd = prevd.data(); P.match = match.data();
+    P.unit_checks = unit_checks; P.seg_out_bytes = seg_out_bytes; P.st = st.data(); P.prevd = prevd.data(); P.prevd2 = (seed & 4) ? nullptr : prevd2.data(); P.match = match.data();
     P.blk_end = blk_end.data(); P.freqs = freqs.data(); P.plans = plans.data(); P.crc = &crc;
     P.tune = deflate_tuning(level, strategy); P.window_bits = window_bits; P.level = level; P.piece_mode = piece_mode;
     P.check_kind = unit_checks ? 3 : 0;
     cusim::set_seed(seed);
     const unsigned ns = P.nseg, nu = P.n_units, nsl = P.n_slots;
     if (P.check_kind) cusim::launch(ns < 3 ? ns : 3, 128, 0, deflate_checksum_kernel, P);
-    if (!P.tune.level0 && !P.tune.huffman_only && !P.tune.rle_only) cusim::launch(ns < 3 ? ns : 3, 32, 0, deflate_chain_kernel, P);
+    if (!P.tune.level0 && !P.tune.huffman_only && !P.tune.rle_only) {
+        cusim::launch(ns < 3 ? ns : 3, 32, 0, deflate_chain_kernel, P);
+        if (P.prevd2) cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_chain2_kernel, P, in_bytes);
+    }
     if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && (seed % 3) == 0)
         cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_match_pairs_kernel, P, in_bytes);
     else if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || (seed & 2))

@@ -6,7 +6,7 @@ import simlib
 from helpers import assert_inflate_parity, fuzz_cases, oracle_inflate, zcomp
 
 
-@pytest.mark.parametrize("D", [1, 4, 32, -9, -8, -1, -2, -3, -4])
+@pytest.mark.parametrize("D", [1, 4, 32, -9, -8, -1, -2, -3, -4, -5, -6])
 def test_sim_golden_gzip(golden, D):
     streams = [c for _, c in golden]
     caps = [len(d) for d, _ in golden]
@@ -20,7 +20,7 @@ def test_sim_golden_gzip(golden, D):
 def test_sim_fuzz_vs_oracle(alice, wbits):
     datas, streams, caps = fuzz_cases(100 + wbits, wbits, 40, alice, sizes=(0, 1, 2, 5, 100, 1000, 5000, 20000))
     ref_outs, ref_st, _ = oracle_inflate(streams, caps, wbits)
-    for D in (1, 8, -9, -1, -2, -3, -4):
+    for D in (1, 8, -9, -1, -2, -3, -4, -5, -6):
         outs, st, ol, cons, _ = simlib.sim_inflate(streams, caps, wbits, D=D, seed=wbits + D)
         assert_inflate_parity(outs, st, ref_outs, ref_st, "wbits %d D %d" % (wbits, D))
 
@@ -34,7 +34,7 @@ def test_sim_segment_mode_checks(alice):
         c = zlib.compressobj(6, zlib.DEFLATED, -15)
         segs.append(c.compress(d) + c.flush(zlib.Z_FULL_FLUSH))
         datas.append(d)
-    for D in (4, -9, -1, -2, -3, -4):
+    for D in (4, -9, -1, -2, -3, -4, -5, -6):
         outs, st, ol, cons, ck = simlib.sim_inflate(segs, [len(d) for d in datas], -15, segment_mode=1, check_kind=3, D=D)
         assert list(st) == [2] * 6
         for i, d in enumerate(datas):
