@@ -266,6 +266,39 @@ __global__ void __launch_bounds__(256) deflate_match_kernel(DeflateParams P, uin
     P.match[g] = P.tune.level0 ? 0u : find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, P.prevd2 ? P.prevd2 + base : nullptr);
 }
 
+// ------------------------------------------------------------------ K2 (sweep)
+// The same per-position search, different geometry: a persistent CTA of THREADS threads sweeps a contiguous chunk of the
+// input, THREADS positions at a time, so that everything its chain walks touch — the 32 KiB of input and the 64 KiB of
+// links behind the sweep — stays in the SM's L1 (with 256-position CTAs dealt round robin, the CTAs resident on one SM
+// work ~37 KB apart and their neighbourhoods do not fit: 78 % L1 hit rate, profiles/r1_deflate_match_v2_ncu.md).
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) deflate_match_sweep_kernel(DeflateParams P, uint64_t total_bytes, uint32_t chunk_bytes) {
+    __shared__ uint32_t s_seg;
+    const uint64_t nchunks = (total_bytes + chunk_bytes - 1) / chunk_bytes;
+    for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const uint64_t g0 = c * chunk_bytes;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t lo = 0, hi = P.nseg;  // last segment with base <= g0
+            while (hi - lo > 1) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (seg_base(P, mid) <= g0) lo = mid; else hi = mid;
+            }
+            s_seg = lo;
+        }
+        __syncthreads();
+        uint32_t seg = s_seg;
+        for (uint32_t off = threadIdx.x; off < chunk_bytes; off += THREADS) {
+            const uint64_t g = g0 + off;
+            if (g >= total_bytes) break;
+            while (seg + 1 < P.nseg && seg_base(P, seg + 1) <= g) seg++;
+            const uint64_t base = seg_base(P, seg);
+            const uint32_t pos = (uint32_t)(g - base);
+            P.match[g] = find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, P.prevd2 ? P.prevd2 + base : nullptr);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ K2 (candidate pairs; experiment, CZ_MATCH_V=2)
 // (Measured on B200: 92 ms per GiB against 77 ms for the simple kernel — every candidate is extended, while find_match()
 // skips the ones that cannot beat the best so far — so it is off by default.)

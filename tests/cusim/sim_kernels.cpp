@@ -98,7 +98,9 @@ extern "C" int sim_deflate(size_t nseg, size_t n_units, const uint8_t *in, const
         cusim::launch(ns < 3 ? ns : 3, 32, 0, deflate_chain_kernel, P);
         if (P.prevd2) cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_chain2_kernel, P, in_bytes);
     }
-    if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && (seed % 3) == 0)
+    if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && (seed % 5) == 0)
+        cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1>, P, in_bytes, 65536u);
+    else if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && (seed % 3) == 0)
         cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_match_pairs_kernel, P, in_bytes);
     else if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || (seed & 2))
         cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_match_kernel, P, in_bytes);
