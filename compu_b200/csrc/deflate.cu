@@ -39,13 +39,22 @@ static inline uint64_t segment_bound(uint64_t len) { return len + len / 2048 + 6
 struct WsLayout {
     uint64_t st, prevd, prevd2, match, blk_end, freqs, plans, pos, total, n_slots, bytes;
 };
+// CZ_MATCH_LINKS=2: build the second-link array and fetch two candidates per step of the match search (measured 124.5 ms per
+// GiB against 110.4 ms for the single-link walk: the speculative loads of the second candidate cost more than the round trip
+// they save). Off by default; the array is only carved out of the workspace when it is on.
+static bool match_two_links() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("CZ_MATCH_LINKS"); v = e ? atoi(e) == 2 : 0; }
+    return v != 0;
+}
+
 static WsLayout ws_layout(uint64_t nseg, uint64_t n_units, uint64_t in_bytes) {
     WsLayout w;
     w.n_slots = (in_bytes >> 14) + nseg + 1;
     uint64_t o = 0;
     w.st = o; o = align_up(o + nseg * sizeof(SegState), 256);
     w.prevd = o; o = align_up(o + 2 * (in_bytes + 8), 256);
-    w.prevd2 = o; o = align_up(o + 2 * (in_bytes + 8), 256);
+    w.prevd2 = o; if (match_two_links()) o = align_up(o + 2 * (in_bytes + 8), 256);
     w.match = o; o = align_up(o + 4 * (in_bytes + 8), 256);
     w.blk_end = o; o = align_up(o + 4 * w.n_slots, 256);
     w.freqs = o; o = align_up(o + 4ull * CZK_FREQ_STRIDE * w.n_slots, 256);
@@ -100,10 +109,7 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
     if (!P.tune.level0 && !P.tune.huffman_only && !P.tune.rle_only) {
         unsigned grid = nseg < (unsigned)ctx->sm_count * 12u ? nseg : (unsigned)ctx->sm_count * 12u;
         czk::deflate_chain_kernel<<<grid, 32, 0, st>>>(P);
-        // CZ_MATCH_LINKS=2: build the second-link array and fetch two candidates per step (measured 124.5 ms per GiB against
-        // 110.4 ms for the single-link walk: the speculative loads of the second candidate cost more than the round trip saved)
-        static int two_links = -1;
-        if (two_links < 0) { const char *e = getenv("CZ_MATCH_LINKS"); two_links = e ? atoi(e) == 2 : 0; }
+        const bool two_links = match_two_links();
         if (two_links) czk::deflate_chain2_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
         else P.prevd2 = nullptr;
     } else P.prevd2 = nullptr;
@@ -184,7 +190,12 @@ struct EngineJob {
 static uint64_t batch_bytes_limit() {
     static uint64_t v = 0;
     if (!v) {
-        v = 1024ull << 20;  // large enough that the warp-per-segment passes (checksum, chains, parse) fill the machine
+        // Large enough that the warp-per-segment passes (checksum, chains, parse) fill the machine. cfg3 end to end on a B200:
+        // 512 MiB / 1 GiB / 2 GiB / 4 GiB batches: 637 / 523 / 502 / 426 ms. A 4 GiB batch needs ~33 GiB per pipeline slot
+        // (input, output bound, workspace): the default on devices with >= 96 GiB, 1 GiB elsewhere.
+        size_t mem_free = 0, mem_total = 0;
+        v = 1024ull << 20;
+        if (cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess && mem_total >= (96ull << 30) && mem_free >= (80ull << 30)) v = 4096ull << 20;
         if (const char *e = getenv("CZ_BATCH_MB")) { long m = atol(e); if (m >= 1 && m <= 8192) v = (uint64_t)m << 20; }
     }
     return v;

@@ -1,6 +1,4 @@
-CZ_MATCH_LINKS=2 python bench.py --workload deflate --mib 1024 --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/r54_deflate_l2.json 2> gpurun_out/r54_deflate_l2.err
-echo "links2: $(grep -o 'ms_per_step": [0-9.]*' gpurun_out/r54_deflate_l2.json)"
-python -m pytest tests/test_gpu_deflate.py tests/test_gpu_multi.py -x -q -m gpu > gpurun_out/r54_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r54_pytest.log
-tail -3 gpurun_out/r54_pytest.log
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r54_deflate_launches.csv python bench.py --workload deflate --mib 1024 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/r54_ncu.log 2>&1
-tail -1 gpurun_out/r54_ncu.log | cut -c1-100
+python bench.py --workload deflate --steps 3 --warmup 2 --no-cpu > gpurun_out/r57_bench_deflate.json 2> gpurun_out/r57_bench_deflate.err
+echo "$(grep -o '"value": [0-9.]*, "unit": "GB/s", "n_gpus"' gpurun_out/r57_bench_deflate.json) $(grep -o '"e2e": {[^}]*}' gpurun_out/r57_bench_deflate.json)"; tail -1 gpurun_out/r57_bench_deflate.err | cut -c1-200
+python -m pytest tests/test_gpu_deflate.py tests/test_gpu_multi.py -x -q -m gpu > gpurun_out/r57_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r57_pytest.log
+tail -3 gpurun_out/r57_pytest.log
