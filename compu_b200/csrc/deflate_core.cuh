@@ -94,9 +94,13 @@ struct MatchScan {
 
 // Examine one candidate `total` bytes back, whose first word (c4) and byte at best_len (cb) are already loaded.
 // Returns true when the search is over (nice length or the longest possible match).
-__host__ __device__ inline bool match_try(MatchScan &m, uint32_t total, uint32_t c4, uint32_t cb, const DeflateTuning &t, uint32_t &chain) {
-    // quick rejects (zlib's order): the byte that would extend the best match, then the first word
-    if (!((m.best_len < 4 || cb == m.cur_end) && c4 == m.cur4)) return false;
+// quick rejects (zlib's order): the byte that would extend the best match, then the first word
+__host__ __device__ inline bool match_passes(const MatchScan &m, uint32_t c4, uint32_t cb) {
+    return (m.best_len < 4 || cb == m.cur_end) && c4 == m.cur4;
+}
+
+// Extend a candidate that passed the quick rejects and update the best match. True when the search is over.
+__host__ __device__ inline bool match_extend(MatchScan &m, uint32_t total, const DeflateTuning &t, uint32_t &chain) {
     const uint8_t *cand = m.cur - total;
     const uint32_t max_len = m.max_len;
     uint32_t l = 4;
@@ -127,6 +131,10 @@ __host__ __device__ inline bool match_try(MatchScan &m, uint32_t total, uint32_t
 #endif
     }
     return false;
+}
+
+__host__ __device__ inline bool match_try(MatchScan &m, uint32_t total, uint32_t c4, uint32_t cb, const DeflateTuning &t, uint32_t &chain) {
+    return match_passes(m, c4, cb) && match_extend(m, total, t, chain);
 }
 
 // Best match for position `pos` of a segment: walk the chain of earlier positions with the same 4-byte hash
@@ -213,6 +221,60 @@ __host__ __device__ inline uint32_t find_match(const uint8_t *seg, uint32_t seg_
     if (best_len < CZK_MIN_MATCH) return 0;
     return best_len | (best_dist << 9);
 }
+
+#if defined(__CUDACC__) || defined(CUSIM)
+// find_match() for 32 positions at once, called by all lanes of a warp (lanes without a position pass valid = false).
+// Same candidates in the same order with the same rules per lane, but the warp alternates between two phases instead of
+// letting every lane run its own loop: WALK — lanes follow their chains until each has found a candidate that passes the
+// quick rejects (or has finished); EXTEND — all those candidates are compared at once. In the per-lane loop the comparison
+// code ran for ~4 lanes at a time (profiles/r1_deflate_match_sweep_ncu.md: 41 % of the kernel's instructions at 4 of 32
+// lanes), because lanes reach a passing candidate at different steps.
+// MEASURED SLOWER (139 ms against 95 ms per GiB, CZ_MATCH_V=6): lanes that have found a candidate wait for the slowest
+// walker of the warp, and that costs more than the batched comparison saves. Kept as an experiment, not the default.
+__device__ inline uint32_t find_match_warp(const uint8_t *seg, uint32_t seg_len, const uint16_t *prevd, uint32_t pos,
+                                           const DeflateTuning &t, bool valid) {
+    uint32_t max_len = 0;
+    if (valid && pos + CZK_MIN_MATCH <= seg_len) { max_len = seg_len - pos; if (max_len > CZK_MAX_MATCH) max_len = CZK_MAX_MATCH; }
+    const uint8_t *cur = seg + pos;
+    MatchScan m;
+    m.cur = cur; m.max_len = max_len;
+    m.cur4 = m.curw1 = m.curw2 = m.curw3 = 0;
+    m.best_len = 0; m.best_dist = 0; m.cur_end = 0;
+    bool walking = max_len >= 4;
+    uint32_t total = 0, d = 0, chain = t.max_chain;
+    if (walking) {
+        m.cur4 = load32u(cur);
+        if (max_len >= 8) m.curw1 = load32u(cur + 4);
+        if (max_len >= 12) m.curw2 = load32u(cur + 8);
+        if (max_len >= 16) m.curw3 = load32u(cur + 12);
+        d = prevd[pos];
+    }
+    for (;;) {
+        bool pend = false;
+        uint32_t pend_total = 0;
+        while (__any_sync(0xffffffffu, walking)) {
+            if (walking) {
+                if (d && chain) {
+                    chain--;
+                    total += d;
+                    if (total > CZK_WINDOW || total > pos) walking = false;
+                    else {
+                        const uint32_t dnext = prevd[pos - total];
+                        const uint32_t c4 = load32u(cur - total);
+                        const uint32_t cb = m.best_len >= 4 ? *(cur - total + m.best_len) : 0u;
+                        if (match_passes(m, c4, cb)) { pend = true; pend_total = total; walking = false; }
+                        d = dnext;
+                    }
+                } else walking = false;
+            }
+        }
+        if (!__any_sync(0xffffffffu, pend)) break;
+        if (pend) walking = !match_extend(m, pend_total, t, chain);
+    }
+    if (m.best_len < CZK_MIN_MATCH) return 0;
+    return m.best_len | (m.best_dist << 9);
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------------------------
 // Tokens: literal = byte << 9 (len field 0), match = len | dist << 9.

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(256) deflate_match_kernel(DeflateParams P, uin
 // input, THREADS positions at a time, so that everything its chain walks touch — the 32 KiB of input and the 64 KiB of
 // links behind the sweep — stays in the SM's L1 (with 256-position CTAs dealt round robin, the CTAs resident on one SM
 // work ~37 KB apart and their neighbourhoods do not fit: 78 % L1 hit rate, profiles/r1_deflate_match_v2_ncu.md).
-template <int THREADS, int MINB>
+template <int THREADS, int MINB, bool WARP_SYNC>
 __global__ void __launch_bounds__(THREADS, MINB) deflate_match_sweep_kernel(DeflateParams P, uint64_t total_bytes, uint32_t chunk_bytes) {
     __shared__ uint32_t s_seg;
     const uint64_t nchunks = (total_bytes + chunk_bytes - 1) / chunk_bytes;
@@ -288,13 +288,16 @@ __global__ void __launch_bounds__(THREADS, MINB) deflate_match_sweep_kernel(Defl
         }
         __syncthreads();
         uint32_t seg = s_seg;
-        for (uint32_t off = threadIdx.x; off < chunk_bytes; off += THREADS) {
-            const uint64_t g = g0 + off;
-            if (g >= total_bytes) break;
-            while (seg + 1 < P.nseg && seg_base(P, seg + 1) <= g) seg++;
+        for (uint32_t off0 = 0; off0 < chunk_bytes; off0 += THREADS) {  // (uniform trip count: find_match_warp is warp-synchronous)
+            const uint64_t g = g0 + off0 + threadIdx.x;
+            const bool valid = off0 + threadIdx.x < chunk_bytes && g < total_bytes;
+            if (valid) while (seg + 1 < P.nseg && seg_base(P, seg + 1) <= g) seg++;
             const uint64_t base = seg_base(P, seg);
-            const uint32_t pos = (uint32_t)(g - base);
-            P.match[g] = find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, P.prevd2 ? P.prevd2 + base : nullptr);
+            const uint32_t pos = valid ? (uint32_t)(g - base) : 0u;
+            uint32_t r;
+            if (WARP_SYNC) r = find_match_warp(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, valid);
+            else r = valid ? find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, P.prevd2 ? P.prevd2 + base : nullptr) : 0u;
+            if (valid) P.match[g] = r;
         }
     }
 }

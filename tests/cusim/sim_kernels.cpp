@@ -99,7 +99,10 @@ extern "C" int sim_deflate(size_t nseg, size_t n_units, const uint8_t *in, const
         if (P.prevd2) cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_chain2_kernel, P, in_bytes);
     }
     if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && (seed % 5) == 0)
-        cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1>, P, in_bytes, 65536u);
+        {
+        if (seed % 2) cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1, true>, P, in_bytes, 65536u);
+        else cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1, false>, P, in_bytes, 65536u);
+    }
     else if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && (seed % 3) == 0)
         cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_match_pairs_kernel, P, in_bytes);
     else if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || (seed & 2))
