@@ -104,22 +104,28 @@ __host__ __device__ inline bool match_extend(MatchScan &m, uint32_t total, const
     const uint8_t *cand = m.cur - total;
     const uint32_t max_len = m.max_len;
     uint32_t l = 4;
-    bool open = true;  // no mismatch found yet
-#define CZK_FM_STEP(cw)                                               \
-    if (open && l + 4 <= max_len) {                                   \
-        const uint32_t x = load32u(cand + l) ^ (cw);                  \
-        if (x) { l += ctz32(x) >> 3; open = false; } else l += 4;     \
-    }
-    CZK_FM_STEP(m.curw1) CZK_FM_STEP(m.curw2) CZK_FM_STEP(m.curw3)
-#undef CZK_FM_STEP
-    if (open) {
+    bool mism = false;  // stopped at a mismatching word (l is final)
+    do {
+        // words 1..3 of the current position come from registers; every exit leaves the few lanes that got here early
+        if (8 > max_len) break;
+        uint32_t x = load32u(cand + 4) ^ m.curw1;
+        if (x) { l = 4 + (ctz32(x) >> 3); mism = true; break; }
+        l = 8;
+        if (12 > max_len) break;
+        x = load32u(cand + 8) ^ m.curw2;
+        if (x) { l = 8 + (ctz32(x) >> 3); mism = true; break; }
+        l = 12;
+        if (16 > max_len) break;
+        x = load32u(cand + 12) ^ m.curw3;
+        if (x) { l = 12 + (ctz32(x) >> 3); mism = true; break; }
+        l = 16;
         while (l + 4 <= max_len) {
-            const uint32_t x = load32u(cand + l) ^ load32u(m.cur + l);
-            if (x) { l += ctz32(x) >> 3; break; }
+            x = load32u(cand + l) ^ load32u(m.cur + l);
+            if (x) { l += ctz32(x) >> 3; mism = true; break; }
             l += 4;
         }
-    }
-    if (l + 4 > max_len)  // fewer than 4 bytes left to compare (or ran to the end): finish byte-wise
+    } while (0);
+    if (!mism)  // fewer than 4 bytes left to compare (or ran to the end): finish byte-wise
         while (l < max_len && cand[l] == m.cur[l]) l++;
     if (l > m.best_len) {
         m.best_len = l;
