@@ -56,7 +56,7 @@ __host__ __device__ inline uint64_t tok_word_off(uint64_t out_off, uint64_t unit
 #define CZK_TOK_STORED 0xC0000000u
 #define CZK_TOK_TAIL 0x20000000u
 #ifndef CZK_LZ_MINB
-#define CZK_LZ_MINB 1
+#define CZK_LZ_MINB 4  // 64 registers: 32 warps per SM (5: 48 registers, 40 warps: 33.3 ms; 6: spills: 40 ms; measured on cfg2)
 #endif
 #define CZK_LZ_SHORT 12  // phase B (token-parallel): matches up to this long are copied by their own lane (8/12/16/24/32 measured: 33.9/32.6/34.0/35.5/38.0 ms)
 
@@ -322,7 +322,7 @@ constexpr size_t inflate_tok_smem_bytes() { return 128 + WARPS * 256 + sizeof(Lc
 // ---------------------------------------------------------------------------------------------------------------
 // Phase B: one warp per unit.
 template <int WARPS, int H>
-__global__ void __launch_bounds__(WARPS * 32, CZK_LZ_MINB) inflate_lz_kernel(TwoPhaseParams Q) {
+__global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_LZ_MINB : 1)) inflate_lz_kernel(TwoPhaseParams Q) {
     const InflateParams &P = Q.base;
     __shared__ uint32_t crc_tab[256 + 34];
     const uint32_t lane = threadIdx.x & 31;
