@@ -115,12 +115,13 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
     } else P.prevd2 = nullptr;
     // Match search geometry. Default (3): persistent CTAs of 1024 threads sweep contiguous chunks, so the 96 KiB neighbourhood
     // of the sweep stays in L1 (94.7 ms per GiB of Markov text at level 6; 4 / 5: 2 x 512 / 2 x 768 threads per SM: 99.3 / 96.5).
+    // 7: the sweep with a flattened walk (one chain step per loop iteration, lanes on different positions: 159 ms);
     // 6: the sweep with the warp-synchronous walk/extend alternation of find_match_warp (139 ms: lanes that found a candidate
     // wait for the slowest walker). CZ_MATCH_V=1: 256-position CTAs dealt round robin (110.4 ms); 2: the candidate-pairs experiment (132.6 ms: it gives up
     // find_match's pruning of candidates that cannot beat the best so far); CZ_MATCH_TILED=1: the tiled experiment.
     static int match_v = -1;
     if (match_v < 0) { const char *e = getenv("CZ_MATCH_V"); match_v = e ? atoi(e) : 3; }
-    if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && match_v >= 3 && match_v <= 6 && !getenv("CZ_MATCH_TILED")) {
+    if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && match_v >= 3 && match_v <= 7 && !getenv("CZ_MATCH_TILED")) {
         const unsigned sms = (unsigned)ctx->sm_count;
         // chunk swept by one CTA: large (the neighbourhood is fetched once per chunk), but at least ~8 chunks per CTA
         static long chunk_kb = -1;
@@ -129,10 +130,11 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
         chunk = (chunk + 65535) & ~65535ull;
         if (chunk < 65536) chunk = 65536;
         if (chunk > (1u << 20) && chunk_kb <= 0) chunk = 1u << 20;
-        if (match_v == 3) czk::deflate_match_sweep_kernel<1024, 1, false><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk);
-        else if (match_v == 6) czk::deflate_match_sweep_kernel<1024, 1, true><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk);
-        else if (match_v == 4) czk::deflate_match_sweep_kernel<512, 2, false><<<sms * 2, 512, 0, st>>>(P, L.in_bytes, (uint32_t)chunk);
-        else czk::deflate_match_sweep_kernel<768, 2, false><<<sms * 2, 768, 0, st>>>(P, L.in_bytes, (uint32_t)chunk);
+        if (match_v == 3) czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk);
+        else if (match_v == 7) czk::deflate_match_sweep_kernel<1024, 1, 2><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk);
+        else if (match_v == 6) czk::deflate_match_sweep_kernel<1024, 1, 1><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk);
+        else if (match_v == 4) czk::deflate_match_sweep_kernel<512, 2, 0><<<sms * 2, 512, 0, st>>>(P, L.in_bytes, (uint32_t)chunk);
+        else czk::deflate_match_sweep_kernel<768, 2, 0><<<sms * 2, 768, 0, st>>>(P, L.in_bytes, (uint32_t)chunk);
     } else if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && match_v == 2 && !getenv("CZ_MATCH_TILED")) {
         czk::deflate_match_pairs_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
     } else if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || !getenv("CZ_MATCH_TILED")) {

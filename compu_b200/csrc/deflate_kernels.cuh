@@ -271,7 +271,14 @@ __global__ void __launch_bounds__(256) deflate_match_kernel(DeflateParams P, uin
 // input, THREADS positions at a time, so that everything its chain walks touch — the 32 KiB of input and the 64 KiB of
 // links behind the sweep — stays in the SM's L1 (with 256-position CTAs dealt round robin, the CTAs resident on one SM
 // work ~37 KB apart and their neighbourhoods do not fit: 78 % L1 hit rate, profiles/r1_deflate_match_v2_ncu.md).
-template <int THREADS, int MINB, bool WARP_SYNC>
+// MODE 0: every lane runs find_match() for its position, the warp reconverges after each position (lanes with short chains
+//         idle while their neighbours walk 16 links: 12.8 of 32 lanes active);
+// MODE 2: the walk is flattened — one loop whose body is ONE chain step; a lane that finishes its position takes its next
+//         one (positions threadIdx.x, + THREADS, ... of the chunk) in the same loop, so the lanes of a warp work on
+//         different positions and stay busy. Same result per position (same candidates, order and rules as find_match).
+//         MEASURED SLOWER (159 ms against 92 ms per GiB): every iteration pays for the set-up, step and extension paths;
+// MODE 1: the warp-synchronous walk/extend alternation of find_match_warp (experiment, slower).
+template <int THREADS, int MINB, int MODE>
 __global__ void __launch_bounds__(THREADS, MINB) deflate_match_sweep_kernel(DeflateParams P, uint64_t total_bytes, uint32_t chunk_bytes) {
     __shared__ uint32_t s_seg;
     const uint64_t nchunks = (total_bytes + chunk_bytes - 1) / chunk_bytes;
@@ -288,16 +295,68 @@ __global__ void __launch_bounds__(THREADS, MINB) deflate_match_sweep_kernel(Defl
         }
         __syncthreads();
         uint32_t seg = s_seg;
-        for (uint32_t off0 = 0; off0 < chunk_bytes; off0 += THREADS) {  // (uniform trip count: find_match_warp is warp-synchronous)
-            const uint64_t g = g0 + off0 + threadIdx.x;
-            const bool valid = off0 + threadIdx.x < chunk_bytes && g < total_bytes;
-            if (valid) while (seg + 1 < P.nseg && seg_base(P, seg + 1) <= g) seg++;
-            const uint64_t base = seg_base(P, seg);
-            const uint32_t pos = valid ? (uint32_t)(g - base) : 0u;
-            uint32_t r;
-            if (WARP_SYNC) r = find_match_warp(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, valid);
-            else r = valid ? find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, P.prevd2 ? P.prevd2 + base : nullptr) : 0u;
-            if (valid) P.match[g] = r;
+        if (MODE == 2) {
+            const DeflateTuning &t = P.tune;
+            uint32_t off = threadIdx.x;
+            bool have = false;
+            MatchScan m;
+            m.cur = nullptr; m.max_len = 0; m.cur4 = m.curw1 = m.curw2 = m.curw3 = 0; m.best_len = m.best_dist = m.cur_end = 0;
+            uint32_t total = 0, d = 0, chain = 0, pos = 0;
+            uint64_t g = 0;
+            const uint16_t *pd = nullptr;
+            for (;;) {
+                if (!have) {
+                    g = g0 + off;
+                    if (off >= chunk_bytes || g >= total_bytes) break;
+                    off += THREADS;
+                    while (seg + 1 < P.nseg && seg_base(P, seg + 1) <= g) seg++;
+                    const uint64_t base = seg_base(P, seg);
+                    const uint32_t n = seg_len(P, seg);
+                    pos = (uint32_t)(g - base);
+                    uint32_t max_len = 0;
+                    if (pos + CZK_MIN_MATCH <= n) { max_len = n - pos; if (max_len > CZK_MAX_MATCH) max_len = CZK_MAX_MATCH; }
+                    if (max_len < 4) { P.match[g] = 0u; continue; }
+                    pd = P.prevd + base;
+                    const uint8_t *cur = P.in + P.seg_off[seg] + pos;
+                    m.cur = cur; m.max_len = max_len;
+                    m.cur4 = load32u(cur);
+                    m.curw1 = max_len >= 8 ? load32u(cur + 4) : 0u;
+                    m.curw2 = max_len >= 12 ? load32u(cur + 8) : 0u;
+                    m.curw3 = max_len >= 16 ? load32u(cur + 12) : 0u;
+                    m.best_len = 0; m.best_dist = 0; m.cur_end = 0;
+                    total = 0; chain = t.max_chain; d = pd[pos];
+                    have = true;
+                }
+                // one link of the chain
+                bool fin = true;
+                if (d && chain) {
+                    chain--;
+                    total += d;
+                    if (!(total > CZK_WINDOW || total > pos)) {
+                        const uint32_t dnext = pd[pos - total];
+                        const uint32_t c4 = load32u(m.cur - total);
+                        const uint32_t cb = m.best_len >= 4 ? *(m.cur - total + m.best_len) : 0u;
+                        fin = match_passes(m, c4, cb) && match_extend(m, total, t, chain);
+                        d = dnext;
+                    }
+                }
+                if (fin) {
+                    P.match[g] = m.best_len >= CZK_MIN_MATCH ? (m.best_len | (m.best_dist << 9)) : 0u;
+                    have = false;
+                }
+            }
+        } else {
+            for (uint32_t off0 = 0; off0 < chunk_bytes; off0 += THREADS) {  // (uniform trip count: find_match_warp is warp-synchronous)
+                const uint64_t g = g0 + off0 + threadIdx.x;
+                const bool valid = off0 + threadIdx.x < chunk_bytes && g < total_bytes;
+                if (valid) while (seg + 1 < P.nseg && seg_base(P, seg + 1) <= g) seg++;
+                const uint64_t base = seg_base(P, seg);
+                const uint32_t pos = valid ? (uint32_t)(g - base) : 0u;
+                uint32_t r;
+                if (MODE == 1) r = find_match_warp(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, valid);
+                else r = valid ? find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, P.prevd2 ? P.prevd2 + base : nullptr) : 0u;
+                if (valid) P.match[g] = r;
+            }
         }
     }
 }

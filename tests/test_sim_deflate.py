@@ -54,7 +54,7 @@ def test_sim_deflate_roundtrip_containers(alice, wbits):
         assert streams[0][:10] == bytes([0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 3])
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3, 5, 10])  # match kernel: 1 tiled, 2 thread-per-position, 3 candidate pairs, 5 sweep (default), 10 sweep over single links... (seed & 4: no second-link array)
+@pytest.mark.parametrize("seed", [1, 2, 3, 5, 10, 20])  # match kernel: 1 tiled, 2 thread-per-position, 3 candidate pairs, 5 sweep (default), 10 sweep over single links... (seed & 4: no second-link array)
 def test_sim_deflate_matches_sequential_model(alice, seed):
     L = model_lib()
     rng = random.Random(11)
@@ -77,7 +77,7 @@ def test_sim_deflate_levels_and_strategies(alice, level, strategy):
     for u, s in zip(units, streams):
         assert dec(s, 15) == u
     # every match kernel makes the same decisions: identical bytes
-    for seed in (2, 3, 5):
+    for seed in (2, 3, 5, 20):
         streams2, st2, _, _, _ = simlib.sim_deflate(units, seg_bytes=16384, level=level, strategy=strategy, window_bits=15, seed=seed)
         assert streams2 == streams and list(st2) == list(st)
 
