@@ -193,12 +193,33 @@ def host_synth(n, seed):
     return out, model
 
 
+
+def deflate_traffic(mib):
+    """DRAM bytes of the dominant kernel (match search) per launch, from the committed ncu capture (profiles/traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return int(json.load(f)["deflate_match_dram_bytes_per_gib"] * mib / 1024)
+    except Exception:
+        return None
+
+
+def cpu_threads():
+    """Host threads for the CPU arm: every CPU this process may run on. (torchrun exports OMP_NUM_THREADS=1 to its workers;
+    the oracle takes its thread count as an argument, so that default does not shrink the baseline to one core.)"""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    e = os.environ.get("CZ_CPU_THREADS")
+    return max(1, int(e)) if e else max(1, n)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU path for this metric (oracle port over zlib 1.3, all host threads)."""
     if rank != 0:
         return
     import oracle
-    threads = oracle.lib().oz_max_threads()
+    threads = cpu_threads()
     # bounded sample of the same workload: enough streams for ~1 s per step on this host
     n = min(args.streams, max(256, 512 * threads))
     plain, _ = host_synth(n, args.seed)
@@ -274,7 +295,7 @@ def run_reference_deflate(args, rank):
     if rank != 0:
         return
     import oracle
-    threads = oracle.lib().oz_max_threads()
+    threads = cpu_threads()
     sample_mib = min(args.mib, max(16, 8 * threads))  # ~1-2 s of CPU work per step at level 6
     plain = host_synth_bytes(sample_mib << 20, args.seed)
     c = CpuDeflate(plain, threads)
@@ -414,7 +435,7 @@ def run_deflate(args, rank, local_rank, world):
         cpu = None
         if not args.no_cpu and world == 1:
             import oracle
-            cthreads = oracle.lib().oz_max_threads()
+            cthreads = cpu_threads()
             sample_mib = min(args.mib, max(16, 8 * cthreads))
             src = plain if plain is not None else d_in[:sample_mib << 20].cpu().numpy()
             c = CpuDeflate(np.ascontiguousarray(src[:sample_mib << 20]), cthreads)
@@ -431,8 +452,8 @@ def run_deflate(args, rank, local_rank, world):
                        "ratio": U / C, "l2": "input per step (%.2f GB) exceeds the 126 MB L2; no flush needed" % (U / 1e9)},
             "e2e": e2e, "gpu_launches": 11 * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(U + C),
-                         "note": "whole kernel chain of one deflate call; the dominant kernel deflate_match_sweep_kernel (53 of ~80 ms per "
+                         "traffic": deflate_traffic(args.mib), "peak_source": peak_src, "algorithmic_bytes_per_launch": int(U + C),
+                         "note": "traffic = DRAM bytes of the dominant kernel alone (ncu); achieved = whole kernel chain of one deflate call; the dominant kernel deflate_match_sweep_kernel (53 of ~80 ms per "
                                  "GiB) is instruction-bound integer code (L1 hit rate 99 %, 79 % issue utilisation at 12.8 active "
                                  "lanes): profiles/r1_deflate_match_sweep_ncu.md, profiles/r1_deflate_4gib_launches.csv"},
             "cpu_baseline": cpu, "clocks": clocks}))
@@ -595,7 +616,7 @@ def main():
         cpu = None
         if not args.no_cpu and world == 1:
             import oracle
-            cthreads = oracle.lib().oz_max_threads()
+            cthreads = cpu_threads()
             ns = min(n, max(256, 512 * cthreads))
             v, secs = cpu_inflate_leg(streams[:ns], cthreads)
             cpu = {"value": v, "unit": UNIT, "cores": cthreads, "kind": "port",

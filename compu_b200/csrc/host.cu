@@ -185,6 +185,9 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
     // big units (megabytes in one stream) go to the warp-per-stream kernel, the rest to the two-phase path
     // (a lane decodes ~4 MB/s, a warp ~26 MB/s: beyond ~256 KiB of output the lane-per-stream path becomes the tail of the batch)
     const uint64_t big_in = 96u << 10, big_out = 256u << 10;
+    static long fast_mb = -1;
+    if (fast_mb < 0) { const char *e = getenv("CZ_INFLATE_FAST_MB"); fast_mb = e ? atol(e) : 0; }
+    const uint64_t fast_head = oe - ob >= (2048ull << 20) ? (uint64_t)fast_mb << 20 : 0;
     std::vector<uint32_t> ids;  // per sub-batch: [small ids..., big ids...], relative to the sub-batch's first unit
     std::vector<size_t> n_small(nsub, 0), n_big(nsub, 0), ids_at(nsub + 1, 0);
     bool any_big = false;
@@ -192,7 +195,10 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
         ids_at[k] = ids.size();
         for (int pass = 0; pass < 2; pass++)
             for (size_t i = cut[k]; i < cut[k + 1]; i++) {
-                const bool big = in_off[u0 + i + 1] - in_off[u0 + i] > big_in || out_off[u0 + i + 1] - out_off[u0 + i] > big_out;
+                // the head of a large shard also takes the warp-per-stream kernel: it hands a 64 KiB stream back after ~2.5 ms
+                // (a lane of the two-phase path needs ~11 ms), so the first device-to-host copies start that much sooner
+                const bool head = fast_head && out_off[u0 + cut[k]] - ob < fast_head;
+                const bool big = head || in_off[u0 + i + 1] - in_off[u0 + i] > big_in || out_off[u0 + i + 1] - out_off[u0 + i] > big_out;
                 if (skip && skip[u0 + i]) { any_big = true; continue; }  // already decoded (speculative split): in neither list
                 if ((int)big == pass) { ids.push_back((uint32_t)(i - cut[k])); (big ? n_big[k] : n_small[k])++; any_big |= big; }
             }
