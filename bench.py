@@ -507,7 +507,7 @@ def main():
     torch.cuda.synchronize()
     t_gen = time.perf_counter() - t0
     plain = d_plain.cpu().numpy()
-    threads = os.cpu_count() or 1
+    threads = cpu_threads()
     t0 = time.perf_counter()
     streams = compress_streams(plain, n, max(1, threads // max(1, world)))
     t_comp = time.perf_counter() - t0
