@@ -107,7 +107,9 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
     const unsigned nseg = P.nseg, nun = P.n_units, nsl = P.n_slots;
     if (P.check_kind) czk::deflate_checksum_kernel<<<nseg < 65535u * 8u ? nseg : 65535u * 8u, 128, 0, st>>>(P);
     if (!P.tune.level0 && !P.tune.huffman_only && !P.tune.rle_only) {
-        unsigned grid = nseg < (unsigned)ctx->sm_count * 12u ? nseg : (unsigned)ctx->sm_count * 12u;
+        static int chain_per_sm = -1;
+        if (chain_per_sm < 0) { const char *e = getenv("CZ_CHAIN_PER_SM"); chain_per_sm = e ? atoi(e) : 12; }
+        unsigned grid = nseg < (unsigned)ctx->sm_count * (unsigned)chain_per_sm ? nseg : (unsigned)ctx->sm_count * (unsigned)chain_per_sm;
         czk::deflate_chain_kernel<<<grid, 32, 0, st>>>(P);
         const bool two_links = match_two_links();
         if (two_links) czk::deflate_chain2_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
@@ -150,7 +152,9 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
         czk::deflate_match_tiled_kernel<<<tiles, CZK_MT_THREADS, smem, st>>>(P);
     }
     {
-        unsigned grid = nseg < (unsigned)ctx->sm_count * 16u ? nseg : (unsigned)ctx->sm_count * 16u;
+        static int parse_per_sm = -1;
+        if (parse_per_sm < 0) { const char *e = getenv("CZ_PARSE_PER_SM"); parse_per_sm = e ? atoi(e) : 16; }
+        unsigned grid = nseg < (unsigned)ctx->sm_count * (unsigned)parse_per_sm ? nseg : (unsigned)ctx->sm_count * (unsigned)parse_per_sm;
         czk::deflate_parse_kernel<<<grid, 32, 0, st>>>(P);
     }
     czk::deflate_hist_kernel<<<nsl, 128, 0, st>>>(P);
