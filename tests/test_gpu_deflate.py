@@ -347,3 +347,42 @@ def test_streaming_encoder_slices_match_one_shot(alice):
     chunked = run([data[o:o + step] for o in range(0, len(data), step)])
     assert len(one) == len(chunked) and np.array_equal(one, chunked)
     assert zlib.decompress(one.tobytes()) == data.tobytes()
+
+
+def test_cfg5_shaped_batch_roundtrip_mixed_sizes_and_classes():
+    """BASELINE.json configs[4] in shape, 1 GiB on the devices present: stream sizes log-uniform in [4 KiB, 16 MiB], the three
+    synthetic classes round robin, every unit deflated (zlib, level 6) and inflated again by the batched entry points with all
+    devices. Size-independent properties: every unit finishes, the round trip is bit-exact, compressed bytes do not depend on
+    the device count (checked when there are >= 2 devices), and a sample of the GPU-encoded streams decodes with zlib (the
+    reference decoder's L0) while a sample of zlib-encoded units decodes on the GPU."""
+    L = _lib.lib()
+    rng = np.random.default_rng(5)
+    total, sizes = 0, []
+    while total < (1 << 30):
+        s = int(np.exp(rng.uniform(np.log(4096), np.log(16 << 20))))
+        sizes.append(s)
+        total += s
+    srcs = {k: _synth_host(k, (max(sizes) + 65535) // 65536 * 65536 * 2, seed=77 + k)[0] for k in (0, 1, 2)}
+    units = []
+    for i, s in enumerate(sizes):
+        src = srcs[i % 3]
+        o = int(rng.integers(0, len(src) - 16 - s))
+        units.append(src[o:o + s].tobytes())
+    mask = (1 << min(L.cz_device_count(), 8)) - 1
+    comp, st = batch.deflate_batch(units, level=6, window_bits=15, devices_mask=mask)
+    assert (st == 2).all()
+    if mask != 1:
+        comp1, st1 = batch.deflate_batch(units, level=6, window_bits=15, devices_mask=1)
+        assert comp1 == comp
+    outs, ist, lens, cons = batch.inflate_batch(comp, [len(u) for u in units], 15, devices_mask=mask)
+    assert (ist == 2).all()
+    assert outs == units
+    assert list(cons) == [len(c) for c in comp]
+    pick = sorted(set([0, len(units) - 1, int(np.argmax(sizes)), int(np.argmin(sizes))] + [int(x) for x in rng.integers(0, len(units), 8)]))
+    for i in pick:
+        assert zlib.decompress(comp[i]) == units[i]
+    zs = [zlib.compress(units[i], 6) for i in pick]
+    outs2, st2, _, _ = batch.inflate_batch(zs, [len(units[i]) for i in pick], 15, devices_mask=mask)
+    assert (st2 == 2).all() and outs2 == [units[i] for i in pick]
+    ratio = sum(len(u) for u in units) / sum(len(c) for c in comp)
+    assert 1.2 < ratio < 4.0, ratio
