@@ -204,7 +204,7 @@ int launch_inflate_count(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_
     P.in = d_in; P.in_off = d_in_off; P.out = nullptr; P.out_off = d_out_off; P.out_lens = d_out_lens; P.statuses = d_statuses;
     P.in_consumed = d_in_consumed; P.checks = nullptr; P.counter = (unsigned long long *)d_ws; P.crc = ctx->d_crc;
     P.n = (uint32_t)n; P.ids = nullptr; P.window_bits = window_bits; P.segment_mode = segment_mode; P.check_kind = 0;
-    P.count_only = 1;
+    P.count_only = 1; P.serial_only = getenv("CZ_PAR_DECODE") ? 0 : 1;
     if (!CZ_CUDA(cudaMemsetAsync(d_ws, 0, 256, st))) return CZ_E_MEM;
     return launch_cfg<1, 8>(st, ctx, P);
 }
@@ -239,6 +239,7 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
     P.in_consumed = d_in_consumed; P.checks = d_checks; P.counter = (unsigned long long *)d_ws; P.crc = ctx->d_crc;
     P.n = (uint32_t)(d_ids ? n_ids : n); P.ids = d_ids;
     P.window_bits = window_bits; P.segment_mode = segment_mode; P.check_kind = check_kind; P.count_only = 0;
+    P.serial_only = getenv("CZ_PAR_DECODE") ? 0 : 1;
     if (!CZ_CUDA(cudaMemsetAsync(d_ws, 0, 256, st))) return CZ_E_MEM;
     InflateCfg c = pick_cfg();
     // big units (one stream is megabytes): one WARP per stream, a single decoder lane feeding warp-cooperative LZ77 rounds —

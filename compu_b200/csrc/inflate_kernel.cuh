@@ -49,6 +49,7 @@ struct InflateParams {
     int32_t segment_mode;     // 1: raw full-flush segments: end of input at a block boundary is success
     int32_t check_kind;       // segment_mode only: bit0 adler, bit1 crc into `checks`
     int32_t count_only;       // inflate_kernel only: produce no output bytes, just sizes / statuses / consumed (out may be null)
+    int32_t serial_only;      // inflate_kernel<1, W> only: 1 = no speculative decode by the idle lanes (experiments)
 };
 
 // litlen table entry (u16): bits 0-3 code length, bits 4-15 payload
@@ -547,8 +548,98 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
             }
         }
 
+        // ---- (5p) D == 1 only: the warp decodes ONE stream, so the 31 lanes that would idle during (5) decode speculatively.
+        // Lane l assumes a literal/length code starts at bit (position + l) and (position + 32 + l) and decodes the whole token
+        // there (code, extra bits, distance code, extra bits: two table look-ups); then the true chain of token starts is
+        // followed through those 64 results with one shuffle per token. A serial lane needs ~250 cycles per token (dependent
+        // look-ups); a round of this costs about as much and yields ~5 tokens on text. Anything unusual — a code longer than the
+        // primary tables, an invalid code, the last bytes of the input — stops the round and is left to the serial decoder (5).
+        // MEASURED (16 zlib-made streams of 8 MiB, tools/big_stream_probe.py): 596 ms against 607 ms serial. A lone warp is bound
+        // by the ~5-cycle dependent issue distance, and a round (two look-ups for 64 offsets, ~5 shuffle hops of the chase,
+        // compaction) is ~35 dependent instructions per token against ~50 for the serial lane. OFF by default (CZ_PAR_DECODE=1).
+        bool par_eob = false;
+        if constexpr (D == 1) {
+            const bool can = !P.serial_only && __shfl_sync(CZK_FULL, (int)(st == SS_DECODE), 0) != 0;
+            if (can) {
+                const uint8_t *ib0 = (const uint8_t *)(uintptr_t)__shfl_sync(CZK_FULL, (unsigned long long)(uintptr_t)in_base, 0);
+                uint64_t cpos = __shfl_sync(CZK_FULL, (unsigned long long)br.consumed(), 0);
+                const uint64_t tbits = __shfl_sync(CZK_FULL, (unsigned long long)br.total, 0);
+                uint32_t nq = __shfl_sync(CZK_FULL, ntok, 0);
+                const uint16_t *lt = my.lit_tab, *dt = my.dist_tab;
+                uint32_t *tokq = my.u.tokens;
+                int stop = 0;  // 1: end of block consumed, 2: next token needs the serial decoder
+                bool did = false;
+                while (!stop && nq < CZK_TOKENS && cpos + 240 <= tbits) {
+                    uint32_t meta[2], tokv[2];
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const uint64_t b = cpos + 32u * h + lane;
+                        const uintptr_t a = (uintptr_t)(ib0 + (b >> 3));
+                        const uint32_t *wp = (const uint32_t *)(a & ~(uintptr_t)3);
+                        const uint32_t sh = (uint32_t)(a & 3) * 8 + (uint32_t)(b & 7);  // 0..31
+                        const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+                        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+                        uint64_t w = (uint64_t)lo | ((uint64_t)hi << 32);  // the 64 bits that start at bit b
+                        uint32_t e = lt[(uint32_t)w & ((1u << CZK_LIT_BITS) - 1u)];
+                        if ((e & 0xfff0u) == CZK_L_LONG) e = decode_long_lit(my, (uint32_t)w & 0x7fffu);
+                        uint32_t pay = e >> 4, tl = e & 15, kind = 0, tv = 0;
+                        if ((e & 0xfff0u) == CZK_L_INVALID) kind = 2;
+                        else if (pay < 0x100) tv = 0x80000000u | (pay << 9) | 1u;
+                        else if (!(pay & 0x800)) kind = pay == 0x100 ? 1 : 2;
+                        else {
+                            w >>= tl;
+                            const uint32_t eb = (pay >> 8) & 7;
+                            const uint32_t len = 3 + (pay & 0xff) + ((uint32_t)w & ((1u << eb) - 1u));
+                            w >>= eb;
+                            uint32_t de = dt[(uint32_t)w & ((1u << CZK_DIST_BITS) - 1u)];
+                            if (de & CZK_D_LONG) de = decode_long_dist(my, (uint32_t)w & 0x7fffu);
+                            if (de & CZK_D_INVALID) kind = 2;
+                            else {
+                                const uint32_t dl = de & 15, deb = (de >> 4) & 15;
+                                w >>= dl;
+                                const uint32_t dist = (((de >> 8) & 3) << deb) + 1 + ((uint32_t)w & ((1u << deb) - 1u));
+                                tl += eb + dl + deb;
+                                tv = (dist << 9) | len;
+                            }
+                        }
+                        meta[h] = tl | (kind << 6);
+                        tokv[h] = tv;
+                    }
+                    // follow the chain of real token starts
+                    uint32_t o = 0, on0 = 0, on1 = 0, cnt = 0;
+                    while (o < 64 && nq + cnt < CZK_TOKENS) {
+                        const uint32_t mm = __shfl_sync(CZK_FULL, o < 32 ? meta[0] : meta[1], o & 31);
+                        const uint32_t kind = mm >> 6;
+                        if (kind == 2) { stop = 2; break; }
+                        if (kind == 1) { o += mm & 63; stop = 1; break; }
+                        if (o < 32) on0 |= 1u << o; else on1 |= 1u << (o - 32);
+                        cnt++;
+                        o += mm & 63;
+                    }
+                    const uint32_t lt_mask = (1u << lane) - 1u;
+                    if ((on0 >> lane) & 1u) tokq[nq + __popc(on0 & lt_mask)] = tokv[0];
+                    if ((on1 >> lane) & 1u) tokq[nq + __popc(on0) + __popc(on1 & lt_mask)] = tokv[1];
+                    nq += cnt;
+                    cpos += o;
+                    did = did || o != 0;
+                }
+                __syncwarp();
+                if (did && lane == 0) {
+                    ntok = nq;
+                    br.seek(cpos >> 3);
+                    br.skip((uint32_t)(cpos & 7));
+                    if (stop == 1) {
+                        par_eob = true;
+                        after_tokens = bfinal ? SS_TRAILER : SS_BLOCK;
+                        if (bfinal) result = ST_FINISHED;
+                        if (!ntok) st = after_tokens;
+                    }
+                }
+            }
+        }
+
         // ---- (5) Huffman decode: D lanes, each its own stream, up to CZK_TOKENS tokens
-        if (st == SS_DECODE) {
+        if (st == SS_DECODE && !par_eob) {
             uint32_t *tok = my.u.tokens;
             after_tokens = SS_DECODE;
             while (ntok < CZK_TOKENS) {

@@ -22,7 +22,7 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
     unsigned long long counter = 0;
     InflateParams P;
     P.in = in; P.in_off = in_off; P.out = out; P.out_off = out_off; P.out_lens = out_lens; P.statuses = statuses;
-    P.in_consumed = in_consumed; P.checks = checks; P.counter = &counter; P.crc = &crc; P.n = (uint32_t)n; P.ids = nullptr; P.count_only = 0;
+    P.in_consumed = in_consumed; P.checks = checks; P.counter = &counter; P.crc = &crc; P.n = (uint32_t)n; P.ids = nullptr; P.count_only = 0; P.serial_only = (seed % 4) == 3;
     P.window_bits = window_bits; P.segment_mode = segment_mode; P.check_kind = check_kind;
     cusim::set_seed(seed);
     switch (D) {
