@@ -14,6 +14,7 @@
 #include <thread>
 
 #include "deflate_kernels.cuh"
+#include <chrono>
 #include "host_common.h"
 
 namespace czh {
@@ -198,12 +199,13 @@ struct EngineJob {
 static uint64_t batch_bytes_limit() {
     static uint64_t v = 0;
     if (!v) {
-        // Large enough that the warp-per-segment passes (checksum, chains, parse) fill the machine. cfg3 end to end on a B200:
-        // 512 MiB / 1 GiB / 2 GiB / 4 GiB batches: 637 / 523 / 502 / 426 ms. A 4 GiB batch needs ~33 GiB per pipeline slot
-        // (input, output bound, workspace): the default on devices with >= 96 GiB, 1 GiB elsewhere.
+        // Large enough that the warp-per-segment passes (checksum, chains, parse) fill the machine, small enough that the copies
+        // of one batch overlap the kernels of the other. cfg3 end to end on a B200 (kernel chains of consecutive batches
+        // serialised, see slot_front): 1 GiB / 2 GiB / 4 GiB batches: 383 / 370 / 418 ms. A 2 GiB batch needs ~17 GiB per
+        // pipeline slot (input, output bound, workspace): the default on devices with >= 64 GiB, 1 GiB elsewhere.
         size_t mem_free = 0, mem_total = 0;
         v = 1024ull << 20;
-        if (cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess && mem_total >= (96ull << 30) && mem_free >= (80ull << 30)) v = 4096ull << 20;
+        if (cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess && mem_total >= (64ull << 30) && mem_free >= (48ull << 30)) v = 2048ull << 20;
         if (const char *e = getenv("CZ_BATCH_MB")) { long m = atol(e); if (m >= 1 && m <= 8192) v = (uint64_t)m << 20; }
     }
     return v;
@@ -246,6 +248,8 @@ struct DeflateSlot {
     PinBuf hmeta, hres, stage;
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t kdone = nullptr;  // the batch's kernels have finished (recorded before the result copies)
+    bool kdone_set = false;
     int dev = -1;
     // batch in flight
     bool busy = false;
@@ -257,15 +261,29 @@ struct DeflateSlot {
         if (dev == d && stream) return true;
         dev = d;
         return CZ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking)) &&
-               CZ_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+               CZ_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming)) &&
+               CZ_CUDA(cudaEventCreateWithFlags(&kdone, cudaEventDisableTiming));
     }
     ~DeflateSlot() {
         if (done) cudaEventDestroy(done);
+        if (kdone) cudaEventDestroy(kdone);
         if (stream) cudaStreamDestroy(stream);
     }
 };
 
-static int slot_front(DeflateSlot &w, DeviceCtx *ctx, EngineJob &J, size_t b) {
+static bool engine_trace() {
+    static int v = -1;
+    if (v < 0) v = getenv("CZ_TRACE") ? 1 : 0;
+    return v != 0;
+}
+static double trace_ms() {
+    static const auto t0 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+#define CZ_TRACE_PT(what, b) do { if (engine_trace()) fprintf(stderr, "[cz] %9.2f ms  %s batch %zu\n", trace_ms(), what, (size_t)(b)); } while (0)
+
+static int slot_front(DeflateSlot &w, DeviceCtx *ctx, EngineJob &J, size_t b, DeflateSlot *prev) {
+    CZ_TRACE_PT("front begin", b);
     const size_t s0 = J.batch_seg[b], s1 = J.batch_seg[b + 1], nseg = s1 - s0;
     w.b = b; w.s0 = s0; w.s1 = s1;
     w.piece_unit.clear(); w.piece_seg.clear();
@@ -309,8 +327,15 @@ static int slot_front(DeflateSlot &w, DeviceCtx *ctx, EngineJob &J, size_t b) {
     L.nseg = nseg; L.n_units = np; L.in_bytes = in_bytes;
     L.level = J.level; L.strategy = J.strategy; L.window_bits = -15; L.piece_mode = 1; L.check_kind = J.check_kind;
     L.packed = true; L.d_unit_out_pos_ret = &d_pos; L.d_total_ret = &d_total;
+    // The kernels of this batch start when those of the previous batch are done: the copies still overlap the other batch's
+    // kernels, but two kernel chains in flight delay each other — the earlier batch's parse / emit passes queue behind the
+    // later batch's match search, and its device-to-host copy with them (traced: the first of two 2 GiB batches finished
+    // after 334 ms instead of ~205 ms).
+    if (prev && prev->kdone_set && !CZ_CUDA(cudaStreamWaitEvent(st, prev->kdone, 0))) return CZ_E_MEM;
     int rc = launch_deflate(st, ctx, L, w.ws.p, w.ws.cap);
     if (rc) return rc;
+    if (!CZ_CUDA(cudaEventRecord(w.kdone, st))) return CZ_E_MEM;
+    w.kdone_set = true;
     // results back: len[np] pos[np] status[np] checks[2np] total segsz[nseg]
     w.res_off_len = 0; w.res_off_pos = 8 * np; w.res_off_stat = 16 * np; w.res_off_chk = align_up(20 * np, 8);
     w.res_off_total = w.res_off_chk + 8 * np; w.res_off_segsz = w.res_off_total + 8;
@@ -324,6 +349,7 @@ static int slot_front(DeflateSlot &w, DeviceCtx *ctx, EngineJob &J, size_t b) {
     if (ok && J.seg_sizes) ok = CZ_CUDA(cudaMemcpyAsync(hr + w.res_off_segsz, dm + m_segsz, 8 * nseg, cudaMemcpyDeviceToHost, st));
     if (!ok || !CZ_CUDA(cudaEventRecord(w.done, st))) return CZ_E_MEM;
     w.busy = true;
+    CZ_TRACE_PT("front enqueued", b);
     return 0;
 }
 
@@ -332,7 +358,9 @@ static int slot_front(DeflateSlot &w, DeviceCtx *ctx, EngineJob &J, size_t b) {
 static int slot_back(DeflateSlot &w, EngineJob &J) {
     if (!w.busy) return 0;
     w.busy = false;
+    CZ_TRACE_PT("back wait", w.b);
     if (!CZ_CUDA(cudaEventSynchronize(w.done))) return CZ_E_MEM;
+    CZ_TRACE_PT("back kernels done", w.b);
     const size_t np = w.np;
     const uint8_t *hr = w.hres.as<uint8_t>();
     const uint64_t *lens = (const uint64_t *)(hr + w.res_off_len), *pos = (const uint64_t *)(hr + w.res_off_pos);
@@ -365,6 +393,7 @@ static int slot_back(DeflateSlot &w, EngineJob &J) {
         for (size_t p = 0; p < np; p++)
             if (dst[p] && lens[p] && !CZ_CUDA(cudaMemcpyAsync(dst[p], w.out.as<uint8_t>() + pos[p], lens[p], cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
         if (!CZ_CUDA(cudaStreamSynchronize(st))) return CZ_E_MEM;
+        CZ_TRACE_PT("back payload copied", w.b);
     } else {
         const uint8_t *sp = w.stage.as<uint8_t>();
 #pragma omp parallel for schedule(static) if (total > (1u << 20))
@@ -406,7 +435,7 @@ static int deflate_engine_one(EngineJob &J, int dev) {
     int rc = 0;
     for (int k = 0; k < 2 && !rc; k++) rc = S->slot[k].init(dev) ? 0 : CZ_E_MEM;
     for (size_t b = 0; b < nb && !rc; b++) {
-        rc = slot_front(S->slot[b & 1], ctx, J, b);                  // its previous batch (b-2) was finished last turn
+        rc = slot_front(S->slot[b & 1], ctx, J, b, b ? &S->slot[(b - 1) & 1] : nullptr);                  // its previous batch (b-2) was finished last turn
         if (!rc && b >= 1) rc = slot_back(S->slot[(b - 1) & 1], J);  // finish b-1 while b runs
     }
     if (!rc && nb) rc = slot_back(S->slot[(nb - 1) & 1], J);

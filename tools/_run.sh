@@ -1,1 +1,3 @@
-ncu --set full --clock-control none --import-source on -k regex:inflate_kernel -c 1 -f -o gpurun_out/r71_big python tools/big_stream_probe.py 16 8 > gpurun_out/r71_ncu.log 2>&1; tail -2 gpurun_out/r71_ncu.log | cut -c1-200
+python -m pytest tests/test_gpu_deflate.py tests/test_gpu_split.py -x -q -m gpu > gpurun_out/r75_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r75_pytest.log
+tail -3 gpurun_out/r75_pytest.log
+python bench.py --workload deflate --no-cpu > gpurun_out/r75_bench_deflate.json 2> gpurun_out/r75_bench_deflate.err; grep -o '"e2e": {[^}]*}' gpurun_out/r75_bench_deflate.json
