@@ -15,6 +15,7 @@
 
 #include "deflate_kernels.cuh"
 #include <chrono>
+#include <map>
 #include "host_common.h"
 
 namespace czh {
@@ -66,6 +67,34 @@ static WsLayout ws_layout(uint64_t nseg, uint64_t n_units, uint64_t in_bytes) {
     return w;
 }
 
+// A side stream (with its fork / join events) per caller stream, created on first use and kept.
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+static SideStream *side_stream_for(cudaStream_t st) {
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, SideStream *> pool;
+    if (getenv("CZ_NO_SIDE_STREAM")) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    auto key = std::make_pair(dev, st);
+    auto it = pool.find(key);
+    if (it != pool.end()) return it->second;
+    SideStream *s = new (std::nothrow) SideStream();
+    if (!s) return nullptr;
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        delete s;
+        s = nullptr;
+    }
+    pool[key] = s;
+    return s;
+}
+
 struct DeflateLaunch {
     const uint8_t *d_in;          // base of the input; segment s starts at d_in + seg_off[s]
     uint8_t *d_out;
@@ -106,7 +135,18 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
     if (L.d_unit_out_pos_ret) *L.d_unit_out_pos_ret = P.unit_out_pos;
     if (L.d_total_ret) *L.d_total_ret = P.total_out;
     const unsigned nseg = P.nseg, nun = P.n_units, nsl = P.n_slots;
-    if (P.check_kind) czk::deflate_checksum_kernel<<<nseg < 65535u * 8u ? nseg : 65535u * 8u, 128, 0, st>>>(P);
+    // The checksum pass only feeds the container framing (K5c), so it runs on a side stream next to the chain and match
+    // kernels (its 128-thread CTAs fit beside the match search's one 1 024-thread CTA per SM) and is joined before K5c.
+    SideStream *side = P.check_kind ? side_stream_for(st) : nullptr;
+    if (P.check_kind) {
+        if (side && CZ_CUDA(cudaEventRecord(side->fork, st)) && CZ_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0))) {
+            czk::deflate_checksum_kernel<<<nseg < 65535u * 8u ? nseg : 65535u * 8u, 128, 0, side->stream>>>(P);
+            if (!CZ_CUDA(cudaEventRecord(side->join, side->stream))) return CZ_E_MEM;
+        } else {
+            side = nullptr;
+            czk::deflate_checksum_kernel<<<nseg < 65535u * 8u ? nseg : 65535u * 8u, 128, 0, st>>>(P);
+        }
+    }
     if (!P.tune.level0 && !P.tune.huffman_only && !P.tune.rle_only) {
         static int chain_per_sm = -1;
         if (chain_per_sm < 0) { const char *e = getenv("CZ_CHAIN_PER_SM"); chain_per_sm = e ? atoi(e) : 12; }
@@ -163,6 +203,7 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
     czk::deflate_seg_layout_kernel<<<(nseg + 31) / 32, 32, 0, st>>>(P);
     czk::deflate_unit_size_kernel<<<(nun + 31) / 32, 32, 0, st>>>(P);
     if (L.packed) czk::deflate_scan_kernel<<<1, 1024, 0, st>>>(P);
+    if (side && !CZ_CUDA(cudaStreamWaitEvent(st, side->join, 0))) return CZ_E_MEM;
     czk::deflate_unit_frame_kernel<<<(nun + 31) / 32, 32, 0, st>>>(P);
     czk::deflate_zero_kernel<<<(nsl + 127) / 128, 128, 0, st>>>(P);
     czk::deflate_emit_kernel<<<nsl, CZK_EMIT_THREADS, 0, st>>>(P);
