@@ -137,10 +137,28 @@ struct InflateWork {
             if (!CZ_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking))) return false;
         return CZ_CUDA(cudaEventCreateWithFlags(&meta_ready, cudaEventDisableTiming));
     }
+    // CZ_TRACE=1: device timeline of the sub-batches (events: start of the shard, H2D done, kernels done, D2H done)
+    struct TraceRec { cudaEvent_t h2d, k, d2h; uint64_t in_bytes, out_bytes; int stream; };
+    cudaEvent_t trace_t0 = nullptr;
+    std::vector<TraceRec> trace;
     bool sync_all() {
         bool ok = true;
         for (int i = 0; i < CZ_INFLATE_STREAMS; i++)
             if (streams[i] && !CZ_CUDA(cudaStreamSynchronize(streams[i]))) ok = false;
+        if (trace_t0) {
+            for (size_t k = 0; k < trace.size(); k++) {
+                float a = 0, b = 0, c = 0;
+                cudaEventElapsedTime(&a, trace_t0, trace[k].h2d);
+                cudaEventElapsedTime(&b, trace_t0, trace[k].k);
+                cudaEventElapsedTime(&c, trace_t0, trace[k].d2h);
+                fprintf(stderr, "[cz] sub-batch %2zu stream %d  in %7.1f MB out %7.1f MB  h2d done %7.2f  kernels done %7.2f  d2h done %7.2f ms\n",
+                        k, trace[k].stream, trace[k].in_bytes / 1e6, trace[k].out_bytes / 1e6, a, b, c);
+                cudaEventDestroy(trace[k].h2d); cudaEventDestroy(trace[k].k); cudaEventDestroy(trace[k].d2h);
+            }
+            cudaEventDestroy(trace_t0);
+            trace_t0 = nullptr;
+            trace.clear();
+        }
         return ok;
     }
 };
@@ -224,12 +242,22 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
     if (!CZ_CUDA(cudaMemcpyAsync(dm, offs.data(), 16 * (n + 1), cudaMemcpyHostToDevice, w.streams[0]))) return CZ_E_MEM;
     if (any_big && !ids.empty() && !CZ_CUDA(cudaMemcpyAsync(dm + m_ids, ids.data(), 4 * ids.size(), cudaMemcpyHostToDevice, w.streams[0]))) return CZ_E_MEM;
     if (!CZ_CUDA(cudaStreamSynchronize(w.streams[0]))) return CZ_E_MEM;  // `offs`/`ids` are stack-lifetime pageable buffers
+    static int tracing = -1;
+    if (tracing < 0) tracing = getenv("CZ_TRACE") ? 1 : 0;
+    if (tracing) {
+        cudaEventCreate(&w.trace_t0);
+        cudaEventRecord(w.trace_t0, w.streams[0]);
+        for (int i = 1; i < CZ_INFLATE_STREAMS; i++) cudaStreamWaitEvent(w.streams[i], w.trace_t0, 0);
+    }
     for (size_t k = 0; k < nsub; k++) {
         cudaStream_t st = w.streams[k % CZ_INFLATE_STREAMS];
         const size_t a = cut[k], b = cut[k + 1], nk = b - a;
+        InflateWork::TraceRec tr = {nullptr, nullptr, nullptr, 0, 0, (int)(k % CZ_INFLATE_STREAMS)};
+        if (tracing) { cudaEventCreate(&tr.h2d); cudaEventCreate(&tr.k); cudaEventCreate(&tr.d2h); }
         const uint64_t ia = offs[a], ibk = offs[b], oa = offs[n + 1 + a], obk = offs[n + 1 + b];
         if (any_big && !n_small[k] && !n_big[k]) continue;  // every unit of this sub-batch was decoded by the speculative split
         if (ibk > ia && !CZ_CUDA(cudaMemcpyAsync(w.in.as<uint8_t>() + ia, in + ib + ia, ibk - ia, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
+        if (tracing) { cudaEventRecord(tr.h2d, st); tr.in_bytes = ibk - ia; tr.out_bytes = obk - oa; }
         const uint32_t *d_ids = any_big ? (const uint32_t *)(dm + m_ids) + ids_at[k] : nullptr;
         uint8_t *wsk = w.ws.as<uint8_t>() + ws_off[k];
         const uint64_t wsk_bytes = ws_off[k + 1] - ws_off[k] - 256;
@@ -243,6 +271,7 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
                                    d_ids ? d_ids + (big ? n_small[k] : 0) : nullptr, big ? n_big[k] : n_small[k], big);
             if (r) return r;
         }
+        if (tracing) cudaEventRecord(tr.k, st);
         if (!skip) {
             if (obk > oa && !CZ_CUDA(cudaMemcpyAsync(out + ob + oa, w.out.as<uint8_t>() + oa, obk - oa, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
         } else {
@@ -261,6 +290,7 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
         if (!CZ_CUDA(cudaMemcpyAsync(w.res_stat + a, dm + m_stat + 4 * a, 4 * nk, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
         if (in_consumed && !CZ_CUDA(cudaMemcpyAsync(w.res_cons + a, dm + m_cons + 8 * a, 8 * nk, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
         if (checks && !CZ_CUDA(cudaMemcpyAsync(w.res_chk + 2 * a, dm + m_chk + 8 * a, 8 * nk, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+        if (tracing) { cudaEventRecord(tr.d2h, st); w.trace.push_back(tr); }
     }
     return 0;
 }

@@ -1,4 +1,5 @@
-python bench.py --workload deflate --no-cpu > gpurun_out/r76_side.json 2> gpurun_out/r76_side.err; echo "side: $(grep -o 'ms_per_step": [0-9.]*' gpurun_out/r76_side.json | head -2 | tr '\n' ' ')"
-CZ_NO_SIDE_STREAM=1 python bench.py --workload deflate --no-cpu > gpurun_out/r76_noside.json 2> gpurun_out/r76_noside.err; echo "no side: $(grep -o 'ms_per_step": [0-9.]*' gpurun_out/r76_noside.json | head -2 | tr '\n' ' ')"
-python -m pytest tests/test_gpu_deflate.py -x -q -m gpu > gpurun_out/r76_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r76_pytest.log
-tail -2 gpurun_out/r76_pytest.log
+for mb in 128 320; do
+CZ_TRACE=1 CZ_INFLATE_FAST_MB=$mb python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/r78_trace_$mb.json 2> gpurun_out/r78_trace_$mb.err
+echo "== fast $mb"; grep "\[cz\]" gpurun_out/r78_trace_$mb.err | tail -19 | cut -c5-130
+grep -o '"e2e": {[^}]*}' gpurun_out/r78_trace_$mb.json | grep -o "ms_per_step.*"
+done
