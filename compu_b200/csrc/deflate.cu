@@ -193,10 +193,15 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
         czk::deflate_match_tiled_kernel<<<tiles, CZK_MT_THREADS, smem, st>>>(P);
     }
     {
+        // one wave of 64-position sub-tiles when the segments fit 16 warps per SM, else 32-position sub-tiles at 28 per SM
         static int parse_per_sm = -1;
-        if (parse_per_sm < 0) { const char *e = getenv("CZ_PARSE_PER_SM"); parse_per_sm = e ? atoi(e) : 16; }
-        unsigned grid = nseg < (unsigned)ctx->sm_count * (unsigned)parse_per_sm ? nseg : (unsigned)ctx->sm_count * (unsigned)parse_per_sm;
-        czk::deflate_parse_kernel<<<grid, 32, 0, st>>>(P);
+        if (parse_per_sm < 0) { const char *e = getenv("CZ_PARSE_PER_SM"); parse_per_sm = e ? atoi(e) : 0; }
+        const unsigned sms = (unsigned)ctx->sm_count;
+        const bool small_tiles = parse_per_sm ? parse_per_sm > 16 : nseg > sms * 16u;
+        const unsigned per_sm = parse_per_sm ? (unsigned)parse_per_sm : (small_tiles ? 28u : 16u);
+        unsigned grid = nseg < sms * per_sm ? nseg : sms * per_sm;
+        if (small_tiles) czk::deflate_parse_kernel<32><<<grid, 32, 0, st>>>(P);
+        else czk::deflate_parse_kernel<64><<<grid, 32, 0, st>>>(P);
     }
     czk::deflate_hist_kernel<<<nsl, 128, 0, st>>>(P);
     czk::deflate_plan_kernel<<<(nsl + 31) / 32, 32, 0, st>>>(P);

@@ -639,10 +639,13 @@ __global__ void __launch_bounds__(CZK_MT_THREADS) deflate_match_tiled_kernel(Def
 // where the previous one left — only has to go until it meets a position the speculative walk also visited, and takes the
 // rest of that sub-tile (and its exit) from the speculation. All lanes then emit the marked tokens with a popcount prefix.
 // Same decisions as parse_segment() in deflate_core.cuh (the sequential statement the tests compare against).
-#define CZK_PARSE_TILE 2048u
-#define CZK_PARSE_SUB 64u
-__device__ __forceinline__ uint32_t parse_pad(uint32_t i) { return i + (i >> 6); }  // one pad entry per sub-tile: no bank conflicts
+// SUB = positions per speculative sub-tile (tile = 32 x SUB). SUB 64: 12.5 KB of shared memory per warp, 16 warps per SM;
+// SUB 32: 6.3 KB, 28 warps per SM — all 4 096 segments of a 4 GiB launch are resident at once instead of two waves of
+// 2 368 (43 -> 25 ms), at the price of twice as many tile set-ups per segment (slower when one wave suffices anyway).
+template <uint32_t CZK_PARSE_SUB>
 __global__ void __launch_bounds__(32) deflate_parse_kernel(DeflateParams P) {
+    constexpr uint32_t CZK_PARSE_TILE = 32u * CZK_PARSE_SUB;
+    auto parse_pad = [](uint32_t i) { return i + i / CZK_PARSE_SUB; };  // one pad entry per sub-tile: no bank conflicts
     __shared__ uint32_t raw_s[CZK_PARSE_TILE + 1];
     __shared__ uint16_t adv_s[CZK_PARSE_TILE + CZK_PARSE_TILE / CZK_PARSE_SUB];
     __shared__ uint32_t vis_s[CZK_PARSE_TILE / 32];
@@ -689,8 +692,10 @@ __global__ void __launch_bounds__(32) deflate_parse_kernel(DeflateParams P) {
                 cur = __shfl_sync(CZK_FULL, nxt, s);
             }
             entry = cur - T;
-            vis_s[2 * lane] = (uint32_t)fin;
-            vis_s[2 * lane + 1] = (uint32_t)(fin >> 32);
+            if (CZK_PARSE_SUB == 64u) {
+                vis_s[2 * lane] = (uint32_t)fin;
+                vis_s[2 * lane + 1] = (uint32_t)(fin >> 32);
+            } else vis_s[lane] = (uint32_t)fin;
             __syncwarp();
             for (uint32_t w = 0; w * 32 < T; w++) {
                 const uint32_t bits = vis_s[w];

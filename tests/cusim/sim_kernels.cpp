@@ -110,7 +110,8 @@ extern "C" int sim_deflate(size_t nseg, size_t n_units, const uint8_t *in, const
         cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_match_kernel, P, in_bytes);
     else
         cusim::launch((unsigned)((in_bytes >> 12) + nseg + 1), CZK_MT_THREADS, deflate_match_tiled_smem(), deflate_match_tiled_kernel, P);
-    cusim::launch(ns < 5 ? ns : 5, 32, 0, deflate_parse_kernel, P);
+    if (seed & 1) cusim::launch(ns < 5 ? ns : 5, 32, 0, deflate_parse_kernel<32>, P);
+    else cusim::launch(ns < 5 ? ns : 5, 32, 0, deflate_parse_kernel<64>, P);
     cusim::launch(nsl, 128, 0, deflate_hist_kernel, P);
     cusim::launch((nsl + 31) / 32, 32, 0, deflate_plan_kernel, P);
     cusim::launch((ns + 31) / 32, 32, 0, deflate_seg_layout_kernel, P);

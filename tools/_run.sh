@@ -1,5 +1,3 @@
-for mb in 128 320; do
-CZ_TRACE=1 CZ_INFLATE_FAST_MB=$mb python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/r78_trace_$mb.json 2> gpurun_out/r78_trace_$mb.err
-echo "== fast $mb"; grep "\[cz\]" gpurun_out/r78_trace_$mb.err | tail -19 | cut -c5-130
-grep -o '"e2e": {[^}]*}' gpurun_out/r78_trace_$mb.json | grep -o "ms_per_step.*"
-done
+python bench.py --workload deflate --no-cpu > gpurun_out/r82_bench_deflate.json 2> gpurun_out/r82_bench_deflate.err; cut -c1-200 gpurun_out/r82_bench_deflate.json; grep -o '"e2e": {[^}]*}' gpurun_out/r82_bench_deflate.json
+python -m pytest tests/test_gpu_deflate.py -x -q -m gpu > gpurun_out/r82_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r82_pytest.log
+tail -2 gpurun_out/r82_pytest.log
