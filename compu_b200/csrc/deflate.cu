@@ -70,7 +70,7 @@ static WsLayout ws_layout(uint64_t nseg, uint64_t n_units, uint64_t in_bytes) {
 // A side stream (with its fork / join events) per caller stream, created on first use and kept.
 struct SideStream {
     cudaStream_t stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, ev_a = nullptr, ev_b = nullptr;
 };
 static SideStream *side_stream_for(cudaStream_t st) {
     static std::mutex mu;
@@ -86,7 +86,9 @@ static SideStream *side_stream_for(cudaStream_t st) {
     if (!s) return nullptr;
     if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_a, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_b, cudaEventDisableTiming) != cudaSuccess) {
         cudaGetLastError();
         delete s;
         s = nullptr;
@@ -138,6 +140,9 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
     // The checksum pass only feeds the container framing (K5c), so it runs on a side stream next to the chain and match
     // kernels (its 128-thread CTAs fit beside the match search's one 1 024-thread CTA per SM) and is joined before K5c.
     SideStream *side = P.check_kind ? side_stream_for(st) : nullptr;
+    unsigned split_at = 0;  // != 0: segments [split_at, nseg) get their chains on the side stream
+    static int match_v = -1;
+    if (match_v < 0) { const char *e = getenv("CZ_MATCH_V"); match_v = e ? atoi(e) : 3; }
     if (P.check_kind) {
         if (side && CZ_CUDA(cudaEventRecord(side->fork, st)) && CZ_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0))) {
             czk::deflate_checksum_kernel<<<nseg < 65535u * 8u ? nseg : 65535u * 8u, 128, 0, side->stream>>>(P);
@@ -151,7 +156,24 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
         static int chain_per_sm = -1;
         if (chain_per_sm < 0) { const char *e = getenv("CZ_CHAIN_PER_SM"); chain_per_sm = e ? atoi(e) : 12; }
         unsigned grid = nseg < (unsigned)ctx->sm_count * (unsigned)chain_per_sm ? nseg : (unsigned)ctx->sm_count * (unsigned)chain_per_sm;
-        czk::deflate_chain_kernel<<<grid, 32, 0, st>>>(P);
+        // Chains in two parts when the launch is more than two waves of resident warps: the first part is exactly one wave, the
+        // second runs on the side stream BESIDE the match search of the first part (its 32-thread CTAs fit next to the match
+        // kernel's one CTA per SM), so only one wave of the chain pass is exposed.
+        // MEASURED: 377 ms against 294 ms per 4 GiB — the chain warps' 17 KB of shared memory each move the SM's L1 / shared
+        // memory split, and the match search loses the L1-resident neighbourhood the sweep geometry is built on. Off unless
+        // CZ_CHAIN_SPLIT is set.
+        const unsigned wave = (unsigned)ctx->sm_count * (unsigned)chain_per_sm;
+        split_at = 0;
+        if (side && match_v == 3 && !getenv("CZ_MATCH_TILED") && !match_two_links() && getenv("CZ_CHAIN_SPLIT") && nseg >= 2 * wave) split_at = wave;
+        if (split_at) {
+            czk::deflate_chain_kernel<<<wave, 32, 0, st>>>(P, 0u, split_at);
+            bool ok = CZ_CUDA(cudaEventRecord(side->ev_a, st)) && CZ_CUDA(cudaStreamWaitEvent(side->stream, side->ev_a, 0));
+            if (!ok) return CZ_E_MEM;
+            unsigned g2 = nseg - split_at < wave ? nseg - split_at : wave;
+            czk::deflate_chain_kernel<<<g2, 32, 0, side->stream>>>(P, split_at, nseg);
+            if (!CZ_CUDA(cudaEventRecord(side->ev_b, side->stream))) return CZ_E_MEM;
+        } else
+        czk::deflate_chain_kernel<<<grid, 32, 0, st>>>(P, 0u, nseg);
         const bool two_links = match_two_links();
         if (two_links) czk::deflate_chain2_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
         else P.prevd2 = nullptr;
@@ -162,8 +184,6 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
     // 6: the sweep with the warp-synchronous walk/extend alternation of find_match_warp (139 ms: lanes that found a candidate
     // wait for the slowest walker). CZ_MATCH_V=1: 256-position CTAs dealt round robin (110.4 ms); 2: the candidate-pairs experiment (132.6 ms: it gives up
     // find_match's pruning of candidates that cannot beat the best so far); CZ_MATCH_TILED=1: the tiled experiment.
-    static int match_v = -1;
-    if (match_v < 0) { const char *e = getenv("CZ_MATCH_V"); match_v = e ? atoi(e) : 3; }
     if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && match_v >= 3 && match_v <= 7 && !getenv("CZ_MATCH_TILED")) {
         const unsigned sms = (unsigned)ctx->sm_count;
         // chunk swept by one CTA: large (the neighbourhood is fetched once per chunk), but at least ~8 chunks per CTA
@@ -173,11 +193,16 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
         chunk = (chunk + 65535) & ~65535ull;
         if (chunk < 65536) chunk = 65536;
         if (chunk > (1u << 20) && chunk_kb <= 0) chunk = 1u << 20;
-        if (match_v == 3) czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk);
-        else if (match_v == 7) czk::deflate_match_sweep_kernel<1024, 1, 2><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk);
-        else if (match_v == 6) czk::deflate_match_sweep_kernel<1024, 1, 1><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk);
-        else if (match_v == 4) czk::deflate_match_sweep_kernel<512, 2, 0><<<sms * 2, 512, 0, st>>>(P, L.in_bytes, (uint32_t)chunk);
-        else czk::deflate_match_sweep_kernel<768, 2, 0><<<sms * 2, 768, 0, st>>>(P, L.in_bytes, (uint32_t)chunk);
+        if (match_v == 3 && split_at) {
+            // first part now, second part once its chains are there
+            czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, split_at);
+            if (!CZ_CUDA(cudaStreamWaitEvent(st, side->ev_b, 0))) return CZ_E_MEM;
+            czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, split_at, nseg);
+        } else if (match_v == 3) czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
+        else if (match_v == 7) czk::deflate_match_sweep_kernel<1024, 1, 2><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
+        else if (match_v == 6) czk::deflate_match_sweep_kernel<1024, 1, 1><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
+        else if (match_v == 4) czk::deflate_match_sweep_kernel<512, 2, 0><<<sms * 2, 512, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
+        else czk::deflate_match_sweep_kernel<768, 2, 0><<<sms * 2, 768, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
     } else if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && match_v == 2 && !getenv("CZ_MATCH_TILED")) {
         czk::deflate_match_pairs_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
     } else if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || !getenv("CZ_MATCH_TILED")) {

@@ -151,11 +151,11 @@ __global__ void __launch_bounds__(128) deflate_checksum_kernel(DeflateParams P) 
 // re-stamped to exactly 32768 behind, which can never look recent before the next sweep. No global re-check is needed.
 #define CZK_CHAIN_SWEEP 16384u
 #define CZK_CHAIN_CHUNK 1024u
-__global__ void __launch_bounds__(32) deflate_chain_kernel(DeflateParams P) {
+__global__ void __launch_bounds__(32) deflate_chain_kernel(DeflateParams P, uint32_t seg_begin, uint32_t seg_end) {
     __shared__ uint16_t head[1u << CZK_HASH_BITS];
     __shared__ __align__(16) uint8_t chunk[CZK_CHAIN_CHUNK + 8];
     const uint32_t lane = threadIdx.x;
-    for (uint32_t seg = blockIdx.x; seg < P.nseg; seg += gridDim.x) {
+    for (uint32_t seg = seg_begin + blockIdx.x; seg < seg_end; seg += gridDim.x) {
         const uint8_t *s = P.in + P.seg_off[seg];
         const uint32_t n = seg_len(P, seg);
         uint16_t *pd = P.prevd + seg_base(P, seg);
@@ -279,11 +279,15 @@ __global__ void __launch_bounds__(256) deflate_match_kernel(DeflateParams P, uin
 //         MEASURED SLOWER (159 ms against 92 ms per GiB): every iteration pays for the set-up, step and extension paths;
 // MODE 1: the warp-synchronous walk/extend alternation of find_match_warp (experiment, slower).
 template <int THREADS, int MINB, int MODE>
-__global__ void __launch_bounds__(THREADS, MINB) deflate_match_sweep_kernel(DeflateParams P, uint64_t total_bytes, uint32_t chunk_bytes) {
+__global__ void __launch_bounds__(THREADS, MINB) deflate_match_sweep_kernel(DeflateParams P, uint64_t total_bytes_all, uint32_t chunk_bytes,
+                                                                            uint32_t seg_begin, uint32_t seg_end) {
     __shared__ uint32_t s_seg;
-    const uint64_t nchunks = (total_bytes + chunk_bytes - 1) / chunk_bytes;
+    // positions of segments [seg_begin, seg_end) (seg_end == 0: every segment)
+    const uint64_t g_begin = seg_end ? seg_base(P, seg_begin) : 0;
+    const uint64_t total_bytes = seg_end ? seg_base(P, seg_end) : total_bytes_all;
+    const uint64_t nchunks = (total_bytes - g_begin + chunk_bytes - 1) / chunk_bytes;
     for (uint64_t c = blockIdx.x; c < nchunks; c += gridDim.x) {
-        const uint64_t g0 = c * chunk_bytes;
+        const uint64_t g0 = g_begin + c * chunk_bytes;
         __syncthreads();
         if (threadIdx.x == 0) {
             uint32_t lo = 0, hi = P.nseg;  // last segment with base <= g0

@@ -95,14 +95,14 @@ extern "C" int sim_deflate(size_t nseg, size_t n_units, const uint8_t *in, const
     const unsigned ns = P.nseg, nu = P.n_units, nsl = P.n_slots;
     if (P.check_kind) cusim::launch(ns < 3 ? ns : 3, 128, 0, deflate_checksum_kernel, P);
     if (!P.tune.level0 && !P.tune.huffman_only && !P.tune.rle_only) {
-        cusim::launch(ns < 3 ? ns : 3, 32, 0, deflate_chain_kernel, P);
+        cusim::launch(ns < 3 ? ns : 3, 32, 0, deflate_chain_kernel, P, 0u, ns);
         if (P.prevd2) cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_chain2_kernel, P, in_bytes);
     }
     if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && (seed % 5) == 0)
         {
-        if (seed % 3 == 2) cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1, 2>, P, in_bytes, 65536u);
-        else if (seed % 2) cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1, 1>, P, in_bytes, 65536u);
-        else cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1, 0>, P, in_bytes, 65536u);
+        if (seed % 3 == 2) cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1, 2>, P, in_bytes, 65536u, 0u, 0u);
+        else if (seed % 2) cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1, 1>, P, in_bytes, 65536u, 0u, 0u);
+        else cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1, 0>, P, in_bytes, 65536u, 0u, 0u);
     }
     else if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && (seed % 3) == 0)
         cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_match_pairs_kernel, P, in_bytes);
