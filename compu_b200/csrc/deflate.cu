@@ -198,7 +198,8 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
             czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, split_at);
             if (!CZ_CUDA(cudaStreamWaitEvent(st, side->ev_b, 0))) return CZ_E_MEM;
             czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, split_at, nseg);
-        } else if (match_v == 3) czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
+        } else if (match_v == 3 && P.prevd2) czk::deflate_match_sweep_kernel<1024, 1, 0, true><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
+        else if (match_v == 3) czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
         else if (match_v == 7) czk::deflate_match_sweep_kernel<1024, 1, 2><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
         else if (match_v == 6) czk::deflate_match_sweep_kernel<1024, 1, 1><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
         else if (match_v == 4) czk::deflate_match_sweep_kernel<512, 2, 0><<<sms * 2, 512, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);

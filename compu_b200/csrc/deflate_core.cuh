@@ -64,8 +64,8 @@ __host__ __device__ inline uint32_t load32u(const uint8_t *p) {
     const uintptr_t a = (uintptr_t)p;
     const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
     const uint32_t sh = (uint32_t)(a & 3) * 8;
-    const uint32_t lo = w[0];
-    const uint32_t hi = sh ? w[1] : 0u;
+    const uint32_t lo = __ldg(w);  // (the encoder only ever reads its input: the non-coherent path is safe)
+    const uint32_t hi = sh ? __ldg(w + 1) : 0u;
     return __funnelshift_r(lo, hi, sh);
 #else
     return load32(p);

@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(256) deflate_match_kernel(DeflateParams P, uin
 //         different positions and stay busy. Same result per position (same candidates, order and rules as find_match).
 //         MEASURED SLOWER (159 ms against 92 ms per GiB): every iteration pays for the set-up, step and extension paths;
 // MODE 1: the warp-synchronous walk/extend alternation of find_match_warp (experiment, slower).
-template <int THREADS, int MINB, int MODE>
+template <int THREADS, int MINB, int MODE, bool LINKS2 = false>
 __global__ void __launch_bounds__(THREADS, MINB) deflate_match_sweep_kernel(DeflateParams P, uint64_t total_bytes_all, uint32_t chunk_bytes,
                                                                             uint32_t seg_begin, uint32_t seg_end) {
     __shared__ uint32_t s_seg;
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(THREADS, MINB) deflate_match_sweep_kernel(Defl
                 const uint32_t pos = valid ? (uint32_t)(g - base) : 0u;
                 uint32_t r;
                 if (MODE == 1) r = find_match_warp(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, valid);
-                else r = valid ? find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, P.prevd2 ? P.prevd2 + base : nullptr) : 0u;
+                else r = valid ? find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, LINKS2 ? P.prevd2 + base : nullptr) : 0u;
                 if (valid) P.match[g] = r;
             }
         }

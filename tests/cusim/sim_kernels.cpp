@@ -102,7 +102,8 @@ extern "C" int sim_deflate(size_t nseg, size_t n_units, const uint8_t *in, const
         {
         if (seed % 3 == 2) cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1, 2>, P, in_bytes, 65536u, 0u, 0u);
         else if (seed % 2) cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1, 1>, P, in_bytes, 65536u, 0u, 0u);
-        else cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1, 0>, P, in_bytes, 65536u, 0u, 0u);
+        else if (P.prevd2) cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1, 0, true>, P, in_bytes, 65536u, 0u, 0u);
+        else cusim::launch(3, 128, 0, deflate_match_sweep_kernel<128, 1, 0, false>, P, in_bytes, 65536u, 0u, 0u);
     }
     else if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && (seed % 3) == 0)
         cusim::launch((unsigned)((in_bytes + 255) / 256 ? (in_bytes + 255) / 256 : 1), 256, 0, deflate_match_pairs_kernel, P, in_bytes);
