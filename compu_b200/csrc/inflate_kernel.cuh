@@ -103,6 +103,7 @@ struct BitReader {
     const uint32_t *words;  // 4-byte aligned base (<= first byte)
     uint32_t mis;           // first byte = (uint8_t*)words + mis
     uint32_t widx, wend;    // words merged into buf so far / number of words that hold stream bytes
+    uint32_t tail_mask;     // the bytes of the last word that belong to the unit
     uint32_t cnt;           // valid bits in buf
     uint32_t nextw;         // words[widx], already loaded (0 past the end)
     uint32_t nextw2;        // words[widx + 1], already loaded: a refill consumes a word that was requested two refills ago, so
@@ -110,7 +111,13 @@ struct BitReader {
     uint64_t buf;
     uint64_t total;         // bits in the unit
 
-    __device__ __forceinline__ uint32_t load(uint32_t i) const { return i < wend ? __ldg(words + i) : 0u; }
+    // Bits past the end of the unit read as ZERO whatever follows it in the packed batch: the last word is masked (a
+    // truncated stream must behave the same alone and between neighbours: its tail decides NEED_INPUT vs data error).
+    __device__ __forceinline__ uint32_t load(uint32_t i) const {
+        uint32_t w = i < wend ? __ldg(words + i) : 0u;
+        if (i + 1 == wend) w &= tail_mask;
+        return w;
+    }
     __device__ __forceinline__ void seek(uint64_t byte_pos) {
         uint64_t a = (uint64_t)mis + byte_pos;
         uint32_t wi = (uint32_t)(a >> 2);
@@ -125,6 +132,8 @@ struct BitReader {
         mis = (uint32_t)((uintptr_t)p & 3);
         words = (const uint32_t *)(p - mis);
         wend = (uint32_t)(((uint64_t)mis + len + 3) >> 2);
+        const uint32_t tb = (uint32_t)(((uint64_t)mis + len) & 3);
+        tail_mask = tb ? (1u << (8 * tb)) - 1u : 0xffffffffu;
         total = len * 8;
         seek(0);
     }
@@ -151,6 +160,12 @@ struct BitReader {
     __device__ __forceinline__ uint64_t consumed() const { return (uint64_t)widx * 32 - 8 * mis - cnt; }
     // true when bits beyond the end of the unit have been consumed; cheap unless the reader is in the last words
     __device__ __forceinline__ bool overrun() const { return widx >= wend && consumed() > total; }
+    // Status when a decoded symbol does not fit the output slot. zlib stops at that symbol having pulled exactly the input
+    // bytes its bits needed, and compu's glue reports Z_OK with avail_in == 0 as NeedInput, avail_in > 0 as NeedOutput
+    // (/root/reference/src/decoder/mod.rs:459-486): the symbol's last bit in the last input byte => NeedInput.
+    __device__ __forceinline__ int out_full_status() const {
+        return ((consumed() + 7) >> 3) >= (total >> 3) ? (int)ST_NEED_INPUT : (int)ST_NEED_OUTPUT;
+    }
     __device__ __forceinline__ uint32_t get_byte() {  // byte-wise header parsing
         refill();
         return get(8);
@@ -351,17 +366,20 @@ __device__ inline uint32_t crc32_bitwise(uint32_t crc, uint32_t byte) {
 }
 
 __device__ inline int parse_gzip_header(BitReader &br) {
+    // zlib's order with a partial header (inflate.c HEAD / FLAGS / TIME / OS): the magic is judged as soon as two bytes are
+    // there, method and flags with four, and only then are the remaining six bytes needed
     uint32_t hcrc = 0xffffffffu;
     uint32_t h[10];
-    for (int i = 0; i < 10; i++) {
-        h[i] = br.get_byte();
-        hcrc = crc32_bitwise(hcrc, h[i]);
-    }
-    if (br.overrun()) return 100;
+    if (br.total < 16) return 100;
+    for (int i = 0; i < 2; i++) { h[i] = br.get_byte(); hcrc = crc32_bitwise(hcrc, h[i]); }
     if (h[0] != 0x1f || h[1] != 0x8b) return ST_E_DATA;  // "incorrect header check"
+    if (br.total < 32) return 100;
+    for (int i = 2; i < 4; i++) { h[i] = br.get_byte(); hcrc = crc32_bitwise(hcrc, h[i]); }
     if (h[2] != 8) return ST_E_DATA;                     // "unknown compression method"
     uint32_t flg = h[3];
     if (flg & 0xe0) return ST_E_DATA;  // "unknown header flags set"
+    if (br.total < 80) return 100;
+    for (int i = 4; i < 10; i++) { h[i] = br.get_byte(); hcrc = crc32_bitwise(hcrc, h[i]); }
     if (flg & 4) {                     // FEXTRA
         uint32_t a = br.get_byte(), b = br.get_byte();
         hcrc = crc32_bitwise(crc32_bitwise(hcrc, a), b);
@@ -449,7 +467,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
 
     // ---- per-slot registers (meaningful on lanes < D)
     BitReader br;
-    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.nextw2 = 0; br.total = 0;
+    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.nextw2 = 0; br.total = 0; br.tail_mask = 0xffffffffu;
     int st = lane < D ? SS_IDLE : SS_EXIT;
     uint32_t unit = 0;
     const uint8_t *in_base = nullptr;
@@ -461,6 +479,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
     int wrap = 0;            // 0 raw, 1 zlib, 2 gzip (resolved per stream)
     uint32_t bfinal = 0, ntok = 0, nlit = 0, ndist = 0, stored_len = 0;
     int after_tokens = SS_DECODE;  // state to enter once the token queue has been drained
+    int full_status = -1;          // >= 0: the decoder stopped at the first token that does not fit the slot; its status
     SlotSmem &my = slots[lane < D ? lane : 0];
 
     for (;;) {
@@ -473,7 +492,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 uint64_t i0 = P.in_off[unit], i1 = P.in_off[unit + 1], o0 = P.out_off[unit], o1 = P.out_off[unit + 1];
                 in_base = P.in + i0; in_len = i1 - i0;
                 out_base = P.out + o0; out_cap = o1 - o0; out_pos = 0; ck_pos = 0;
-                adler = 1; crc = 0; ntok = 0; bfinal = 0; result = 0;
+                adler = 1; crc = 0; ntok = 0; bfinal = 0; result = 0; full_status = -1;
                 br.init(in_base, in_len);
                 st = SS_HEADER;
             }
@@ -522,6 +541,8 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                     st = SS_BUILD;
                 } else if (btype == 2) {
                     int r = parse_dynamic_header(br, my, nlit, ndist);
+                    // a verdict reached with bits past the end of the input is not a verdict: zlib would still be waiting
+                    if (r == ST_E_DATA && br.consumed() > br.total) r = 100;
                     if (r == 0) st = SS_BUILD;
                     else { result = r == 100 ? ST_NEED_INPUT : r; st = SS_FINISH; }
                 } else { result = ST_E_DATA; st = SS_FINISH; }  // "invalid block type"
@@ -642,6 +663,10 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
         if (st == SS_DECODE && !par_eob) {
             uint32_t *tok = my.u.tokens;
             after_tokens = SS_DECODE;
+            // zlib stops at the first symbol that does not fit the output slot, with exactly that symbol's bits consumed;
+            // the queue must not run ahead of it (the status and the consumed-byte count depend on where it stops)
+            uint64_t room = out_cap - out_pos;
+            const bool track = ntok == 0;  // (tokens queued by the speculative path (5p) are not accounted for)
             while (ntok < CZK_TOKENS) {
                 br.refill();
                 uint32_t e = my.lit_tab[br.peek(CZK_LIT_BITS)];
@@ -651,6 +676,10 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                     br.skip(e & 15);
                     if (br.overrun()) { result = ST_NEED_INPUT; after_tokens = SS_FINISH; break; }
                     tok[ntok++] = 0x80000000u | (pay << 9) | 1u;
+                    if (track) {
+                        if (room == 0) { full_status = br.out_full_status(); after_tokens = SS_FINISH; break; }
+                        room--;
+                    }
                     continue;
                 }
                 if (!(pay & 0x800)) {
@@ -685,6 +714,10 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 br.skip(deb);
                 if (br.overrun()) { result = ST_NEED_INPUT; after_tokens = SS_FINISH; break; }
                 tok[ntok++] = (dist << 9) | len;
+                if (track) {
+                    if (len > room) { full_status = br.out_full_status(); after_tokens = SS_FINISH; break; }
+                    room -= len;
+                }
             }
             st = after_tokens == SS_DECODE ? SS_DECODE : (ntok ? SS_DECODE : after_tokens);
         }
@@ -766,7 +799,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 if ((int)lane == s) {
                     out_pos = opos + total;
                     ntok = 0;
-                    if (err) { result = err; st = SS_FINISH; }
+                    if (err) { result = (err == ST_NEED_OUTPUT && full_status >= 0) ? full_status : err; st = SS_FINISH; }
                     else st = after_tokens;
                 }
             }

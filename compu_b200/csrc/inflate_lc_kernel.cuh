@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lc_kernel(InflateParams P)
     __syncthreads();
 
     BitReader br;
-    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.nextw2 = 0; br.total = 0;
+    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.nextw2 = 0; br.total = 0; br.tail_mask = 0xffffffffu;
     uint32_t llim[8], dlim[8];
     lc_limits_reset(llim); lc_limits_reset(dlim);
     int st = SS_IDLE;
@@ -316,6 +316,8 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lc_kernel(InflateParams P)
                     st = SS_BUILD;
                 } else if (btype == 2) {
                     int r = lc_parse_dynamic(br, my, nlit, ndist);
+                    // a verdict reached with bits past the end of the input is not a verdict: zlib would still be waiting
+                    if (r == ST_E_DATA && br.consumed() > br.total) r = 100;
                     if (r == 0) st = SS_BUILD;
                     else { result = r == 100 ? ST_NEED_INPUT : r; st = SS_FINISH; }
                 } else { result = ST_E_DATA; st = SS_FINISH; }  // "invalid block type"
@@ -357,7 +359,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lc_kernel(InflateParams P)
                 br.skip(cl);
                 if (sym < 256) {  // literal
                     if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
-                    if (pos >= cap) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
+                    if (pos >= cap) { result = br.out_full_status(); st = SS_FINISH; break; }
                     out[pos++] = (uint8_t)sym;
                     if (ckmode & 1) { s1 += sym; s2 += s1; adl_n--; }
                     if (ckmode & 2) crc = (crc >> 8) ^ crc_tab[(crc ^ sym) & 0xff];
@@ -393,7 +395,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lc_kernel(InflateParams P)
                 br.skip(deb);
                 if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
                 // zlib order (inflate.c MATCH): output space first, then "invalid distance too far back"
-                if (pos >= cap) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
+                if (pos >= cap) { result = br.out_full_status(); st = SS_FINISH; break; }
                 if ((uint64_t)dist > pos) { result = ST_E_DATA; st = SS_FINISH; break; }
                 uint32_t n = len;
                 if (pos + n > cap) n = (uint32_t)(cap - pos);
@@ -439,7 +441,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lc_kernel(InflateParams P)
                 }
                 adl_n -= n;
                 pos += n;
-                if (n < len) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
+                if (n < len) { result = br.out_full_status(); st = SS_FINISH; break; }
             }
         }
 

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
     __syncthreads();
 
     BitReader br;
-    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.nextw2 = 0; br.total = 0;
+    br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.nextw2 = 0; br.total = 0; br.tail_mask = 0xffffffffu;
     uint32_t llim[8], dlim[8];
     lc_limits_reset(llim); lc_limits_reset(dlim);
     int st = SS_IDLE;
@@ -153,6 +153,8 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
                     st = SS_BUILD;
                 } else if (btype == 2) {
                     int r = lc_parse_dynamic(br, my, nlit_sym, ndist_sym);
+                    // a verdict reached with bits past the end of the input is not a verdict: zlib would still be waiting
+                    if (r == ST_E_DATA && br.consumed() > br.total) r = 100;
                     if (r == 0) st = SS_BUILD;
                     else { result = r == 100 ? ST_NEED_INPUT : r; st = SS_FINISH; }
                 } else { result = ST_E_DATA; st = SS_FINISH; }  // "invalid block type"
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
                 if (sym < 256) {  // literal
                     if (slow) {
                         if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
-                        if (pos >= cap) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
+                        if (pos >= cap) { result = br.out_full_status(); st = SS_FINISH; break; }
                     }
                     pos++;
                     lit |= sym << (8 * nlit);
@@ -238,14 +240,14 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
                 if (slow) {
                     if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
                     // zlib order (inflate.c MATCH): output space first, then "invalid distance too far back"
-                    if (pos >= cap) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
+                    if (pos >= cap) { result = br.out_full_status(); st = SS_FINISH; break; }
                     if (pos + n > cap) n = (uint32_t)(cap - pos);
                 }
                 if ((uint64_t)dist > pos) { result = ST_E_DATA; st = SS_FINISH; break; }
                 CZK_FLUSH_LIT();
                 CZK_PUT(n | (dist << 9));
                 pos += n;
-                if (n < len) { result = ST_NEED_OUTPUT; st = SS_FINISH; break; }
+                if (n < len) { result = br.out_full_status(); st = SS_FINISH; break; }
             }
         }
 

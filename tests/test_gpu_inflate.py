@@ -208,3 +208,23 @@ def test_cta_tile_cases_vs_oracle(alice):
                 assert list(cons) == [len(s) for s in streams]
     finally:
         L.cz_tune_inflate_lz(0, 100)
+
+
+def test_truncated_tail_does_not_see_the_neighbour(alice):
+    """Bits past the end of a unit read as zero whatever follows it in the packed batch (a truncated stream decides NEED_INPUT
+    vs data error from its own bytes only) — every kernel family."""
+    base = [zcomp(b"a" * 5000, 6, 31), zcomp(alice[:3000], 6, 31), zcomp(bytes(range(256)) * 8, 9, 31), zcomp(alice[:70000], 6, 31)]
+    streams, caps = [], []
+    for s, cap in zip(base, (5000, 3000, 2048, 70000)):
+        for cut in range(11, len(s) - 1, max(1, len(s) // 37)):
+            streams.append(s[:cut]); caps.append(cap)
+            streams.append(b"\xff" * 7); caps.append(16)
+    ref_outs, ref_st, _ = oracle_inflate(streams, caps, 31)
+    L = _lib.lib()
+    try:
+        for cfg in [(-2, 14), (-1, 14), (1, 8), (4, 7), (-9, 8)]:
+            L.cz_tune_inflate(*cfg)
+            outs, st, lens, cons = batch.inflate_batch(streams, caps, 31)
+            assert_inflate_parity(outs, st, ref_outs, ref_st, "cfg %s" % (cfg,))
+    finally:
+        L.cz_tune_inflate(-2, 14)

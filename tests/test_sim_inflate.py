@@ -64,3 +64,19 @@ def test_sim_cta_tile_cases(alice):
         outs, st, ol, cons, _ = simlib.sim_inflate(ss, cc, wbits, D=-4, seed=7 + wbits)
         assert_inflate_parity(outs, st, ref_outs, ref_st, "cta wbits %d" % wbits)
         assert list(st) == [2] * len(idx)
+
+
+def test_sim_truncated_tail_does_not_see_the_neighbour(alice):
+    """Bits past the end of a unit must read as zero whatever follows it in the packed batch: a truncated stream decides
+    NEED_INPUT vs data error from its own bytes only (found by a wider fuzz: a 24-byte truncated gzip stream followed by
+    another unit reported -3 instead of 0)."""
+    base = [zcomp(b"a" * 5000, 6, 31), zcomp(alice[:3000], 6, 31), zcomp(bytes(range(256)) * 8, 9, 31)]
+    streams, caps = [], []
+    for s, cap in zip(base, (5000, 3000, 2048)):
+        for cut in range(11, len(s) - 1, max(1, len(s) // 23)):
+            streams.append(s[:cut]); caps.append(cap)
+            streams.append(b"\xff" * 7); caps.append(16)     # a neighbour full of one bits
+    ref_outs, ref_st, _ = oracle_inflate(streams, caps, 31)
+    for D in (1, 8, -1, -2, -3):
+        outs, st, ol, cons, _ = simlib.sim_inflate(streams, caps, 31, D=D, seed=3)
+        assert_inflate_parity(outs, st, ref_outs, ref_st, "D %d" % D)
