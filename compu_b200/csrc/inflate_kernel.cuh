@@ -113,16 +113,15 @@ struct BitReader {
 
     // Bits past the end of the unit read as ZERO whatever follows it in the packed batch: the last word is masked (a
     // truncated stream must behave the same alone and between neighbours: its tail decides NEED_INPUT vs data error).
-    __device__ __forceinline__ uint32_t load(uint32_t i) const {
-        uint32_t w = i < wend ? __ldg(words + i) : 0u;
-        if (i + 1 == wend) w &= tail_mask;
-        return w;
-    }
+    // (the mask is applied when a word enters the bit buffer, not when it is loaded: the look-ahead words must not be
+    // touched before they are needed, or every refill waits for the load it has just issued)
+    __device__ __forceinline__ uint32_t load(uint32_t i) const { return i < wend ? __ldg(words + i) : 0u; }
+    __device__ __forceinline__ uint32_t masked(uint32_t w, uint32_t i) const { return i + 1 == wend ? (w & tail_mask) : w; }
     __device__ __forceinline__ void seek(uint64_t byte_pos) {
         uint64_t a = (uint64_t)mis + byte_pos;
         uint32_t wi = (uint32_t)(a >> 2);
         uint32_t sh = (uint32_t)(a & 3) * 8;
-        buf = (uint64_t)(load(wi) >> sh);
+        buf = (uint64_t)(masked(load(wi), wi) >> sh);
         cnt = 32 - sh;
         widx = wi + 1;
         nextw = load(widx);
@@ -140,7 +139,7 @@ struct BitReader {
     // after refill(): cnt >= 33
     __device__ __forceinline__ void refill() {
         if (cnt <= 32) {
-            buf |= (uint64_t)nextw << cnt;
+            buf |= (uint64_t)masked(nextw, widx) << cnt;
             cnt += 32;
             widx++;
             nextw = nextw2;
