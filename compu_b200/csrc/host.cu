@@ -704,7 +704,9 @@ static int decoder_pass(DecoderState *s) {
         int rc = inflate_batch_host(1, s->in.as<uint8_t>(), in_off, s->out.as<uint8_t>(), out_off, &out_len, &status, &consumed,
                                     s->window_bits, 0, nullptr, 1u << s->dev);
         if (rc) return rc;
-        if (status == CZ_DECODE_NEED_OUTPUT) { cap *= 2; continue; }
+        // A full slot means "grow and retry" whatever the status says: when the symbol that did not fit ends in the last staged
+        // byte the kernels report NeedInput, as zlib would (avail_in == 0), but here the slot size is our own guess
+        if (status == CZ_DECODE_NEED_OUTPUT || (status == CZ_DECODE_NEED_INPUT && out_len >= cap)) { cap *= 2; continue; }
         s->out_len = (size_t)out_len;
         s->out_cap_hint = cap;
         if (status == CZ_DECODE_FINISHED) { s->done = true; s->stream_bytes = (size_t)consumed; }

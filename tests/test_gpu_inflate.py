@@ -228,3 +228,36 @@ def test_truncated_tail_does_not_see_the_neighbour(alice):
             assert_inflate_parity(outs, st, ref_outs, ref_st, "cfg %s" % (cfg,))
     finally:
         L.cz_tune_inflate(-2, 14)
+
+
+def test_streaming_decoder_slot_growth_byte_by_byte():
+    """The streaming decoder re-inflates what is staged into a slot of its own choosing (64 KiB at first) and must grow it
+    whenever it fills up — also when the kernels report NeedInput for a full slot (the symbol that did not fit ends in the last
+    staged byte, zlib's avail_in == 0 case). Feeding a highly compressible 200 000-byte stream one byte at a time walks through
+    every staged-prefix length, including that one."""
+    data = (b"a" * 70000) + bytes(range(256)) * 100 + (b"xyz" * 35000)
+    for wb, mode in ((15, ZlibMode.Zlib), (-15, ZlibMode.Deflate), (31, ZlibMode.Gzip)):
+        stream = zcomp(data, 9, wb)
+        dec = Interface.zlib_cuda(mode)
+        assert dec is not None
+        out = bytearray()
+        window = bytearray(1 << 16)
+        status = None
+        for i in range(len(stream)):
+            piece = stream[i:i + 1]
+            while True:
+                r = dec.decode(piece, window)
+                out += window[:len(window) - r.output_remain]
+                piece = piece[len(piece) - r.input_remain:]
+                status = r.status
+                if status != DecodeStatus.NeedOutput:
+                    break
+            assert not isinstance(status, DecodeError), (wb, i, status)
+        for _ in range(8):  # drain (zlib-style callers loop until Finished)
+            if status == DecodeStatus.Finished:
+                break
+            r = dec.decode(b"", window)
+            out += window[:len(window) - r.output_remain]
+            status = r.status
+        assert status == DecodeStatus.Finished and bytes(out) == data, (wb, status, len(out))
+        dec.close()
