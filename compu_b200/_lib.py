@@ -23,6 +23,7 @@ SIGNATURES = {
     "cz_device_count": (ci, []),
     "cz_version": (ctypes.c_char_p, []),
     "cz_last_error": (ctypes.c_char_p, []),
+    "cz_launch_count": (u64, []),
     "cz_host_alloc": (vp, [sz]),
     "cz_host_free": (None, [vp]),
     "cz_decoder_new": (vp, [ci]),
@@ -53,6 +54,7 @@ SIGNATURES = {
     "cz_split_stats": (None, [vp, vp]),
     "cz_profile_enable": (None, [ci]),
     "cz_profile_read": (ci, [vp, vp]),
+    "cz_profile_read_deflate": (ci, [vp, vp]),
     "cz_adler32_combine": (u32, [u32, u32, u64]),
     "cz_crc32_combine": (u32, [u32, u32, u64]),
     "cz_synth_model_bytes": (u64, []),

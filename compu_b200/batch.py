@@ -68,7 +68,9 @@ def deflate_segmented(data, level=6, window_bits=15, strategy=0, segment_bytes=0
     out = np.empty(cap + 16, dtype=np.uint8)
     out_len = ctypes.c_uint64(0)
     nseg = ctypes.c_uint64(0)
-    idx_cap = n // (64 * 1024) + 8
+    seg = int(segment_bytes) if segment_bytes else (1 << 20)
+    seg = min(max(seg, 4096), int(L.cz_deflate_max_segment()))  # the library clamps the same way
+    idx_cap = (n + seg - 1) // seg + 2
     idx = np.zeros(idx_cap, dtype=np.uint64)
     rc = L.cz_deflate_segmented(_p(src), n, _p(out), cap, ctypes.byref(out_len), level, window_bits, strategy, segment_bytes,
                                 devices_mask, _p(idx), idx_cap, ctypes.byref(nseg))

@@ -75,7 +75,8 @@ struct SideStream {
 static SideStream *side_stream_for(cudaStream_t st) {
     static std::mutex mu;
     static std::map<std::pair<int, cudaStream_t>, SideStream *> pool;
-    if (getenv("CZ_NO_SIDE_STREAM")) return nullptr;
+    static const bool no_side = getenv("CZ_NO_SIDE_STREAM") != nullptr;
+    if (no_side) return nullptr;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
     std::lock_guard<std::mutex> lk(mu);
@@ -96,6 +97,10 @@ static SideStream *side_stream_for(cudaStream_t st) {
     pool[key] = s;
     return s;
 }
+
+struct DeflateProf { cudaEvent_t e0, m0, m1, e1; };
+static std::vector<DeflateProf> g_dprof;
+static std::mutex g_dprof_mu;
 
 struct DeflateLaunch {
     const uint8_t *d_in;          // base of the input; segment s starts at d_in + seg_off[s]
@@ -137,19 +142,26 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
     if (L.d_unit_out_pos_ret) *L.d_unit_out_pos_ret = P.unit_out_pos;
     if (L.d_total_ret) *L.d_total_ret = P.total_out;
     const unsigned nseg = P.nseg, nun = P.n_units, nsl = P.n_slots;
+    // bench.py's per-kernel timing (cz_profile_enable): events around the whole chain and around the match search
+    const bool prof = profiling_on();
+    DeflateProf pr = {nullptr, nullptr, nullptr, nullptr};
+    if (prof) {
+        cudaEventCreate(&pr.e0); cudaEventCreate(&pr.m0); cudaEventCreate(&pr.m1); cudaEventCreate(&pr.e1);
+        cudaEventRecord(pr.e0, st);
+    }
     // The checksum pass only feeds the container framing (K5c), so it runs on a side stream next to the chain and match
     // kernels (its 128-thread CTAs fit beside the match search's one 1 024-thread CTA per SM) and is joined before K5c.
     SideStream *side = P.check_kind ? side_stream_for(st) : nullptr;
     unsigned split_at = 0;  // != 0: segments [split_at, nseg) get their chains on the side stream
-    static int match_v = -1;
-    if (match_v < 0) { const char *e = getenv("CZ_MATCH_V"); match_v = e ? atoi(e) : 3; }
+    static const int match_v = [] { const char *e = getenv("CZ_MATCH_V"); return e ? atoi(e) : 3; }();
+    static const bool match_tiled = getenv("CZ_MATCH_TILED") != nullptr, chain_split = getenv("CZ_CHAIN_SPLIT") != nullptr;
     if (P.check_kind) {
         if (side && CZ_CUDA(cudaEventRecord(side->fork, st)) && CZ_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0))) {
-            czk::deflate_checksum_kernel<<<nseg < 65535u * 8u ? nseg : 65535u * 8u, 128, 0, side->stream>>>(P);
+            CZ_KL(czk::deflate_checksum_kernel<<<nseg < 65535u * 8u ? nseg : 65535u * 8u, 128, 0, side->stream>>>(P));
             if (!CZ_CUDA(cudaEventRecord(side->join, side->stream))) return CZ_E_MEM;
         } else {
             side = nullptr;
-            czk::deflate_checksum_kernel<<<nseg < 65535u * 8u ? nseg : 65535u * 8u, 128, 0, st>>>(P);
+            CZ_KL(czk::deflate_checksum_kernel<<<nseg < 65535u * 8u ? nseg : 65535u * 8u, 128, 0, st>>>(P));
         }
     }
     if (!P.tune.level0 && !P.tune.huffman_only && !P.tune.rle_only) {
@@ -164,27 +176,28 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
         // CZ_CHAIN_SPLIT is set.
         const unsigned wave = (unsigned)ctx->sm_count * (unsigned)chain_per_sm;
         split_at = 0;
-        if (side && match_v == 3 && !getenv("CZ_MATCH_TILED") && !match_two_links() && getenv("CZ_CHAIN_SPLIT") && nseg >= 2 * wave) split_at = wave;
+        if (side && match_v == 3 && !match_tiled && !match_two_links() && chain_split && nseg >= 2 * wave) split_at = wave;
         if (split_at) {
-            czk::deflate_chain_kernel<<<wave, 32, 0, st>>>(P, 0u, split_at);
+            CZ_KL(czk::deflate_chain_kernel<<<wave, 32, 0, st>>>(P, 0u, split_at));
             bool ok = CZ_CUDA(cudaEventRecord(side->ev_a, st)) && CZ_CUDA(cudaStreamWaitEvent(side->stream, side->ev_a, 0));
             if (!ok) return CZ_E_MEM;
             unsigned g2 = nseg - split_at < wave ? nseg - split_at : wave;
-            czk::deflate_chain_kernel<<<g2, 32, 0, side->stream>>>(P, split_at, nseg);
+            CZ_KL(czk::deflate_chain_kernel<<<g2, 32, 0, side->stream>>>(P, split_at, nseg));
             if (!CZ_CUDA(cudaEventRecord(side->ev_b, side->stream))) return CZ_E_MEM;
         } else
-        czk::deflate_chain_kernel<<<grid, 32, 0, st>>>(P, 0u, nseg);
+        CZ_KL(czk::deflate_chain_kernel<<<grid, 32, 0, st>>>(P, 0u, nseg));
         const bool two_links = match_two_links();
-        if (two_links) czk::deflate_chain2_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
+        if (two_links) CZ_KL(czk::deflate_chain2_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes));
         else P.prevd2 = nullptr;
     } else P.prevd2 = nullptr;
+    if (prof) cudaEventRecord(pr.m0, st);
     // Match search geometry. Default (3): persistent CTAs of 1024 threads sweep contiguous chunks, so the 96 KiB neighbourhood
     // of the sweep stays in L1 (94.7 ms per GiB of Markov text at level 6; 4 / 5: 2 x 512 / 2 x 768 threads per SM: 99.3 / 96.5).
     // 7: the sweep with a flattened walk (one chain step per loop iteration, lanes on different positions: 159 ms);
     // 6: the sweep with the warp-synchronous walk/extend alternation of find_match_warp (139 ms: lanes that found a candidate
     // wait for the slowest walker). CZ_MATCH_V=1: 256-position CTAs dealt round robin (110.4 ms); 2: the candidate-pairs experiment (132.6 ms: it gives up
     // find_match's pruning of candidates that cannot beat the best so far); CZ_MATCH_TILED=1: the tiled experiment.
-    if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && match_v >= 3 && match_v <= 7 && !getenv("CZ_MATCH_TILED")) {
+    if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && match_v >= 3 && match_v <= 7 && !match_tiled) {
         const unsigned sms = (unsigned)ctx->sm_count;
         // chunk swept by one CTA: large (the neighbourhood is fetched once per chunk), but at least ~8 chunks per CTA
         static long chunk_kb = -1;
@@ -195,19 +208,19 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
         if (chunk > (1u << 20) && chunk_kb <= 0) chunk = 1u << 20;
         if (match_v == 3 && split_at) {
             // first part now, second part once its chains are there
-            czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, split_at);
+            CZ_KL(czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, split_at));
             if (!CZ_CUDA(cudaStreamWaitEvent(st, side->ev_b, 0))) return CZ_E_MEM;
-            czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, split_at, nseg);
-        } else if (match_v == 3 && P.prevd2) czk::deflate_match_sweep_kernel<1024, 1, 0, true><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
-        else if (match_v == 3) czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
-        else if (match_v == 7) czk::deflate_match_sweep_kernel<1024, 1, 2><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
-        else if (match_v == 6) czk::deflate_match_sweep_kernel<1024, 1, 1><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
-        else if (match_v == 4) czk::deflate_match_sweep_kernel<512, 2, 0><<<sms * 2, 512, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
-        else czk::deflate_match_sweep_kernel<768, 2, 0><<<sms * 2, 768, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u);
-    } else if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && match_v == 2 && !getenv("CZ_MATCH_TILED")) {
-        czk::deflate_match_pairs_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
-    } else if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || !getenv("CZ_MATCH_TILED")) {
-        czk::deflate_match_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes);
+            CZ_KL(czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, split_at, nseg));
+        } else if (match_v == 3 && P.prevd2) CZ_KL(czk::deflate_match_sweep_kernel<1024, 1, 0, true><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u));
+        else if (match_v == 3) CZ_KL(czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u));
+        else if (match_v == 7) CZ_KL(czk::deflate_match_sweep_kernel<1024, 1, 2><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u));
+        else if (match_v == 6) CZ_KL(czk::deflate_match_sweep_kernel<1024, 1, 1><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u));
+        else if (match_v == 4) CZ_KL(czk::deflate_match_sweep_kernel<512, 2, 0><<<sms * 2, 512, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u));
+        else CZ_KL(czk::deflate_match_sweep_kernel<768, 2, 0><<<sms * 2, 768, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u));
+    } else if (!(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only) && match_v == 2 && !match_tiled) {
+        CZ_KL(czk::deflate_match_pairs_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes));
+    } else if (P.tune.level0 || P.tune.huffman_only || P.tune.rle_only || !match_tiled) {
+        CZ_KL(czk::deflate_match_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes));
     } else {
         static bool configured[64] = {};
         const size_t smem = czk::deflate_match_tiled_smem();
@@ -216,9 +229,10 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
             configured[ctx->dev & 63] = true;
         }
         const unsigned tiles = (unsigned)((L.in_bytes >> 12) + L.nseg + 1);
-        czk::deflate_match_tiled_kernel<<<tiles, CZK_MT_THREADS, smem, st>>>(P);
+        CZ_KL(czk::deflate_match_tiled_kernel<<<tiles, CZK_MT_THREADS, smem, st>>>(P));
     }
     {
+    if (prof) cudaEventRecord(pr.m1, st);
         // one wave of 64-position sub-tiles when the segments fit 16 warps per SM, else 32-position sub-tiles at 28 per SM
         static int parse_per_sm = -1;
         if (parse_per_sm < 0) { const char *e = getenv("CZ_PARSE_PER_SM"); parse_per_sm = e ? atoi(e) : 0; }
@@ -226,18 +240,23 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
         const bool small_tiles = parse_per_sm ? parse_per_sm > 16 : nseg > sms * 16u;
         const unsigned per_sm = parse_per_sm ? (unsigned)parse_per_sm : (small_tiles ? 28u : 16u);
         unsigned grid = nseg < sms * per_sm ? nseg : sms * per_sm;
-        if (small_tiles) czk::deflate_parse_kernel<32><<<grid, 32, 0, st>>>(P);
-        else czk::deflate_parse_kernel<64><<<grid, 32, 0, st>>>(P);
+        if (small_tiles) CZ_KL(czk::deflate_parse_kernel<32><<<grid, 32, 0, st>>>(P));
+        else CZ_KL(czk::deflate_parse_kernel<64><<<grid, 32, 0, st>>>(P));
     }
-    czk::deflate_hist_kernel<<<nsl, 128, 0, st>>>(P);
-    czk::deflate_plan_kernel<<<(nsl + 31) / 32, 32, 0, st>>>(P);
-    czk::deflate_seg_layout_kernel<<<(nseg + 31) / 32, 32, 0, st>>>(P);
-    czk::deflate_unit_size_kernel<<<(nun + 31) / 32, 32, 0, st>>>(P);
-    if (L.packed) czk::deflate_scan_kernel<<<1, 1024, 0, st>>>(P);
+    CZ_KL(czk::deflate_hist_kernel<<<nsl, 128, 0, st>>>(P));
+    CZ_KL(czk::deflate_plan_kernel<<<(nsl + 31) / 32, 32, 0, st>>>(P));
+    CZ_KL(czk::deflate_seg_layout_kernel<<<(nseg + 31) / 32, 32, 0, st>>>(P));
+    CZ_KL(czk::deflate_unit_size_kernel<<<(nun + 31) / 32, 32, 0, st>>>(P));
+    if (L.packed) CZ_KL(czk::deflate_scan_kernel<<<1, 1024, 0, st>>>(P));
     if (side && !CZ_CUDA(cudaStreamWaitEvent(st, side->join, 0))) return CZ_E_MEM;
-    czk::deflate_unit_frame_kernel<<<(nun + 31) / 32, 32, 0, st>>>(P);
-    czk::deflate_zero_kernel<<<(nsl + 127) / 128, 128, 0, st>>>(P);
-    czk::deflate_emit_kernel<<<nsl, CZK_EMIT_THREADS, 0, st>>>(P);
+    CZ_KL(czk::deflate_unit_frame_kernel<<<(nun + 31) / 32, 32, 0, st>>>(P));
+    CZ_KL(czk::deflate_zero_kernel<<<(nsl + 127) / 128, 128, 0, st>>>(P));
+    CZ_KL(czk::deflate_emit_kernel<<<nsl, CZK_EMIT_THREADS, 0, st>>>(P));
+    if (prof) {
+        cudaEventRecord(pr.e1, st);
+        std::lock_guard<std::mutex> lk(g_dprof_mu);
+        g_dprof.push_back(pr);
+    }
     return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
 }
 
@@ -478,8 +497,11 @@ static int slot_back(DeflateSlot &w, EngineJob &J) {
 struct DeviceSlots {
     std::mutex mu;        // one host thread at a time drives a device's pipeline slots
     DeflateSlot slot[2];
-    PinBuf part_buf;      // multi-device path: payloads of units that straddle a device boundary
 };
+// multi-device path: payloads of units that straddle a device boundary are gathered through a pinned buffer that belongs
+// to the CALL (borrowed from a bounded per-device pool), so concurrent callers never share it
+struct PartBuf { PinBuf buf; };
+static DevicePool<PartBuf, 1> g_part_pool;
 static std::mutex g_dslots_mu;
 static DeviceSlots *g_dslots[64] = {};  // created on first use, kept for the life of the process (buffers are reused)
 static DeviceSlots *device_slots(int dev) {
@@ -560,7 +582,10 @@ static int deflate_engine(EngineJob &J, uint32_t mask) {
         std::vector<uint32_t> unit_ids;
         std::vector<uint8_t> whole;
         std::vector<uint64_t> seg_sizes;
+        PartBuf *part = nullptr;
+        int dev = 0;
         int rc = 0;
+        ~Part() { g_part_pool.release(dev, part); }
     };
     std::vector<Part> parts(nd);
     for (size_t k = 0; k < nd; k++) {
@@ -596,12 +621,13 @@ static int deflate_engine(EngineJob &J, uint32_t mask) {
                 }
                 priv_off[i + 1] = priv_off[i] + b;
             }
-            if (priv_off[n] && !S->part_buf.reserve(priv_off[n] + 64)) { Pk.rc = CZ_E_MEM; return; }
+            Pk.dev = dev;
+            if (priv_off[n] && (!(Pk.part = g_part_pool.acquire(dev)) || !Pk.part->buf.reserve(priv_off[n] + 64))) { Pk.rc = CZ_E_MEM; return; }
             Pk.J.dst.resize(n); Pk.J.dst_cap.resize(n);
             for (size_t i = 0; i < n; i++) {
                 const uint32_t u = Pk.unit_ids[i];
                 if (Pk.whole[i]) { Pk.J.dst[i] = J.dst[u]; Pk.J.dst_cap[i] = J.dst_cap[u]; }
-                else { Pk.J.dst[i] = S->part_buf.as<uint8_t>() + priv_off[i]; Pk.J.dst_cap[i] = priv_off[i + 1] - priv_off[i]; }
+                else { Pk.J.dst[i] = Pk.part->buf.as<uint8_t>() + priv_off[i]; Pk.J.dst_cap[i] = priv_off[i + 1] - priv_off[i]; }
             }
             plan_job(Pk.J);
             Pk.rc = deflate_engine_one(Pk.J, dev);
@@ -669,6 +695,22 @@ static bool valid_wbits_enc(int wb) { return wb == -15 || wb == 15 || wb == 31; 
 }  // namespace czh
 
 using namespace czh;
+
+extern "C" int cz_profile_read_deflate(double *ms_match, double *ms_chain) {
+    std::lock_guard<std::mutex> lk(g_dprof_mu);
+    double a = 0, b = 0;
+    int k = 0;
+    for (DeflateProf &r : g_dprof) {
+        float x = 0, y = 0;
+        if (cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&x, r.m0, r.m1) == cudaSuccess &&
+            cudaEventElapsedTime(&y, r.e0, r.e1) == cudaSuccess) { a += x; b += y; k++; }
+        cudaEventDestroy(r.e0); cudaEventDestroy(r.m0); cudaEventDestroy(r.m1); cudaEventDestroy(r.e1);
+    }
+    g_dprof.clear();
+    if (ms_match) *ms_match = a;
+    if (ms_chain) *ms_chain = b;
+    return k;
+}
 
 extern "C" uint64_t cz_deflate_max_segment(void) { return CZK_SEG_MAX; }
 extern "C" uint64_t cz_deflate_segment_bound(uint64_t n) { return segment_bound(n); }
@@ -825,6 +867,7 @@ struct EncoderState {
     bool header_done = false, finished = false, error = false;
     uint32_t adler = 1, crc = 0;
     uint64_t total_in = 0;
+    int last_rank = -4;    // zlib's RANK(last_flush); deflateReset leaves last_flush = -2
 };
 
 extern "C" void *cz_encoder_new(int level, int window_bits, int mem_level, int strategy) {
@@ -848,6 +891,7 @@ extern "C" void *cz_encoder_reset(void *state) {
     s->in_len = s->pend_len = s->pend_pos = 0;  // keeps the pinned allocations
     s->header_done = s->finished = s->error = false;
     s->adler = 1; s->crc = 0; s->total_in = 0;
+    s->last_rank = -4;
     return s;
 }
 
@@ -912,7 +956,18 @@ extern "C" cz_result cz_encode(void *state, const uint8_t *in, size_t in_len, ui
     r.output_remain = out_len;
     r.status = CZ_ENCODE_ERROR;
     if (!s || s->error || op < CZ_OP_PROCESS || op > CZ_OP_FINISH) return r;
-    if (s->finished && in_len) return r;  // zlib: deflate() after Z_STREAM_END with new input is Z_STREAM_ERROR
+    // The calls zlib's deflate() refuses before it touches the stream, in its order (deflate.c: deflate()), mapped like
+    // src/encoder/mod.rs:356-369 maps them: Z_STREAM_ERROR -> Error, Z_BUF_ERROR -> NeedOutput, nothing consumed.
+    if (s->finished && op != CZ_OP_FINISH) return r;                     // FINISH_STATE && flush != Z_FINISH
+    if (out_len == 0) { r.status = CZ_ENCODE_NEED_OUTPUT; return r; }    // avail_out == 0
+    {
+        const int rank = op == CZ_OP_PROCESS ? 0 : op == CZ_OP_FLUSH ? 4 : 8;  // RANK(Z_NO_FLUSH / Z_SYNC_FLUSH / Z_FINISH)
+        const int old_rank = s->last_rank;
+        s->last_rank = rank;
+        // no pending output, no new input and a flush no stronger than the last one: zlib has nothing to do
+        if (s->pend_pos == s->pend_len && in_len == 0 && rank <= old_rank && op != CZ_OP_FINISH) { r.status = CZ_ENCODE_NEED_OUTPUT; return r; }
+    }
+    if (s->finished && in_len) { r.status = CZ_ENCODE_NEED_OUTPUT; return r; }  // FINISH_STATE && avail_in != 0: Z_BUF_ERROR
     if (in_len) {
         if (!s->in.reserve(s->in_len + in_len + 16, true, s->in_len)) { s->error = true; return r; }
         memcpy(s->in.as<uint8_t>() + s->in_len, in, in_len);
@@ -922,6 +977,8 @@ extern "C" cz_result cz_encode(void *state, const uint8_t *in, size_t in_len, ui
     while (!s->finished && s->in_len >= kEncoderSlice + (op == CZ_OP_PROCESS ? 0 : 1)) {
         if (encoder_emit(s, kEncoderSlice, false, false)) { s->error = true; return r; }
     }
+    // (a Flush that finds undelivered output and no new input only drains: the compressed bytes must not depend on the
+    //  sizes of the caller's output buffers, tests/encoder.rs:56-57, 65-66)
     if (!s->finished && ((op == CZ_OP_FLUSH && (s->in_len || s->pend_pos == s->pend_len)) || op == CZ_OP_FINISH)) {
         int rc = encoder_emit(s, s->in_len, op == CZ_OP_FLUSH, op == CZ_OP_FINISH);
         if (rc) { s->error = true; return r; }

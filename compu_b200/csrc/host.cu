@@ -30,6 +30,9 @@ bool cuda_ok(cudaError_t e, const char *what) {
     return false;
 }
 
+static std::atomic<uint64_t> g_launches{0};
+void count_launches(unsigned k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
+
 static std::mutex g_ctx_mu;
 static DeviceCtx g_ctx[64];
 static int g_ndev = -1;
@@ -128,14 +131,17 @@ struct InflateWork {
     int32_t *res_stat = nullptr;
     uint32_t *res_chk = nullptr;
     cudaStream_t streams[CZ_INFLATE_STREAMS] = {};
-    cudaEvent_t meta_ready = nullptr;
     int dev = -1;
     bool init(int d) {
         if (dev == d && streams[0]) return true;
         dev = d;
         for (int i = 0; i < CZ_INFLATE_STREAMS; i++)
             if (!CZ_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking))) return false;
-        return CZ_CUDA(cudaEventCreateWithFlags(&meta_ready, cudaEventDisableTiming));
+        return true;
+    }
+    ~InflateWork() {
+        for (int i = 0; i < CZ_INFLATE_STREAMS; i++)
+            if (streams[i]) cudaStreamDestroy(streams[i]);
     }
     // CZ_TRACE=1: device timeline of the sub-batches (events: start of the shard, H2D done, kernels done, D2H done)
     struct TraceRec { cudaEvent_t h2d, k, d2h; uint64_t in_bytes, out_bytes; int stream; };
@@ -203,8 +209,7 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
     // big units (megabytes in one stream) go to the warp-per-stream kernel, the rest to the two-phase path
     // (a lane decodes ~4 MB/s, a warp ~26 MB/s: beyond ~256 KiB of output the lane-per-stream path becomes the tail of the batch)
     const uint64_t big_in = 96u << 10, big_out = 256u << 10;
-    static long fast_mb = -1;
-    if (fast_mb < 0) { const char *e = getenv("CZ_INFLATE_FAST_MB"); fast_mb = e ? atol(e) : 0; }
+    static const long fast_mb = [] { const char *e = getenv("CZ_INFLATE_FAST_MB"); return e ? atol(e) : 0l; }();
     const uint64_t fast_head = oe - ob >= (2048ull << 20) ? (uint64_t)fast_mb << 20 : 0;
     std::vector<uint32_t> ids;  // per sub-batch: [small ids..., big ids...], relative to the sub-batch's first unit
     std::vector<size_t> n_small(nsub, 0), n_big(nsub, 0), ids_at(nsub + 1, 0);
@@ -242,8 +247,7 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
     if (!CZ_CUDA(cudaMemcpyAsync(dm, offs.data(), 16 * (n + 1), cudaMemcpyHostToDevice, w.streams[0]))) return CZ_E_MEM;
     if (any_big && !ids.empty() && !CZ_CUDA(cudaMemcpyAsync(dm + m_ids, ids.data(), 4 * ids.size(), cudaMemcpyHostToDevice, w.streams[0]))) return CZ_E_MEM;
     if (!CZ_CUDA(cudaStreamSynchronize(w.streams[0]))) return CZ_E_MEM;  // `offs`/`ids` are stack-lifetime pageable buffers
-    static int tracing = -1;
-    if (tracing < 0) tracing = getenv("CZ_TRACE") ? 1 : 0;
+    static const int tracing = getenv("CZ_TRACE") ? 1 : 0;
     if (tracing) {
         cudaEventCreate(&w.trace_t0);
         cudaEventRecord(w.trace_t0, w.streams[0]);
@@ -330,7 +334,9 @@ struct CountWork {
         dev = d;
         return CZ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     }
+    ~CountWork() { if (stream) cudaStreamDestroy(stream); }
 };
+static DevicePool<CountWork, 1> g_count_pool;
 
 // sizes / statuses / consumed bytes of the pieces [in_off[j], in_off[j+1]) of `in`; dev_in_valid: the device copy is current
 static int inflate_count_host(CountWork &w, int dev, const uint8_t *in, uint64_t in_bytes, bool &dev_in_valid, size_t n,
@@ -380,7 +386,7 @@ static long host_header_len(const uint8_t *p, uint64_t n, int window_bits, int &
     return o <= n ? (long)o : -1;
 }
 
-static uint64_t g_split_ok = 0, g_split_tried = 0;  // statistics (cz_split_stats)
+static std::atomic<uint64_t> g_split_ok{0}, g_split_tried{0};  // statistics (cz_split_stats)
 
 static uint64_t huge_unit_bytes() {
     static uint64_t v = 0;
@@ -414,7 +420,10 @@ static bool inflate_split_speculative(const uint8_t *in, uint64_t in_len, uint8_
     }
     if (cut.size() < 3) return false;  // fewer than two verified-able pieces: nothing to gain
     const int dev = devices_mask ? __builtin_ctz(devices_mask) : 0;
-    static thread_local CountWork cw;
+    CountWork *cwp = g_count_pool.acquire(dev);
+    if (!cwp) return false;
+    struct Lease { CountWork *w; int dev; ~Lease() { g_count_pool.release(dev, w); } } lease{cwp, dev};
+    CountWork &cw = *cwp;
     bool dev_in_valid = false;
     int prev = 0;
     cudaGetDevice(&prev);
@@ -513,7 +522,8 @@ int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint
     std::vector<uint8_t> skip;
     struct Done { size_t i; uint64_t len, cons; int32_t st; };
     std::vector<Done> done;
-    if (!segment_mode && !checks && !getenv("CZ_NO_SPLIT")) {
+    static const bool no_split = getenv("CZ_NO_SPLIT") != nullptr;
+    if (!segment_mode && !checks && !no_split) {
         for (size_t i = 0; i < n; i++) {
             if (in_off[i + 1] - in_off[i] < huge_unit_bytes()) continue;
             Done d{i, 0, 0, 0};
@@ -527,7 +537,15 @@ int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint
             }
         }
     }
-    static thread_local InflateWork works[32];
+    // one work object (streams, device and pinned buffers) per device, borrowed from a bounded per-device pool
+    static DevicePool<InflateWork, 2> pool;
+    InflateWork *works[32] = {};
+    struct Lease {
+        InflateWork **w; DevicePool<InflateWork, 2> *p;
+        ~Lease() { for (int d = 0; d < 32; d++) if (w[d]) p->release(d, w[d]); }
+    } lease{works, &pool};
+    for (int d : devs)
+        if (!(works[d] = pool.acquire(d))) { set_error("out of memory"); return CZ_E_MEM; }
     int prev = 0;
     cudaGetDevice(&prev);
     std::vector<size_t> cuts;
@@ -535,12 +553,12 @@ int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint
     int rc = 0;
     // enqueue every shard first (copies and kernels of different devices overlap), then wait for all
     for (size_t k = 0; k < devs.size() && !rc; k++)
-        rc = inflate_shard(works[devs[k]], devs[k], cuts[k], cuts[k + 1], in, in_off, out, out_off, out_lens, statuses,
+        rc = inflate_shard(*works[devs[k]], devs[k], cuts[k], cuts[k + 1], in, in_off, out, out_off, out_lens, statuses,
                            in_consumed, window_bits, segment_mode, checks, skip.empty() ? nullptr : skip.data());
     for (size_t k = 0; k < devs.size(); k++) {
-        if (!works[devs[k]].streams[0]) continue;
+        if (!works[devs[k]]->streams[0]) continue;
         cudaSetDevice(devs[k]);
-        InflateWork &w = works[devs[k]];
+        InflateWork &w = *works[devs[k]];
         if (!w.sync_all() && !rc) rc = CZ_E_MEM;
         if (!rc && w.res_n) {
             memcpy(out_lens + w.res_u0, w.res_lens, 8 * w.res_n);
@@ -567,6 +585,7 @@ using namespace czh;
 extern "C" int cz_device_count(void) { return usable_device_count(); }
 extern "C" const char *cz_version(void) { return "compu-b200 0.1 (sm_100a)"; }
 extern "C" const char *cz_last_error(void) { return g_err; }
+extern "C" uint64_t cz_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" void *cz_host_alloc(size_t bytes) {
     void *p = nullptr;
@@ -595,8 +614,8 @@ extern "C" const char *cz_describe_error(int32_t code) {
 }
 
 extern "C" void cz_split_stats(uint64_t *tried, uint64_t *split) {
-    if (tried) *tried = g_split_tried;
-    if (split) *split = g_split_ok;
+    if (tried) *tried = g_split_tried.load();
+    if (split) *split = g_split_ok.load();
 }
 
 extern "C" int cz_partition_by_bytes(size_t n, const uint64_t *offsets, int parts, uint64_t *cuts) {
@@ -623,7 +642,12 @@ extern "C" int cz_inflate_batch_ptrs(size_t n, const uint8_t *const *in_ptrs, co
     // gather into the packed form (pinned), run, scatter
     std::vector<uint64_t> ioff(n + 1, 0), ooff(n + 1, 0), lens(n, 0);
     for (size_t i = 0; i < n; i++) { ioff[i + 1] = ioff[i] + in_lens[i]; ooff[i + 1] = ooff[i] + out_caps[i]; }
-    static thread_local PinBuf pin_in, pin_out;
+    struct PinPair { PinBuf in, out; };
+    static DevicePool<PinPair, 2> pin_pool;
+    PinPair *pp = pin_pool.acquire(0);
+    if (!pp) return CZ_E_MEM;
+    struct Lease { PinPair *p; DevicePool<PinPair, 2> *pool; ~Lease() { pool->release(0, p); } } lease{pp, &pin_pool};
+    PinBuf &pin_in = pp->in, &pin_out = pp->out;
     if (!pin_in.reserve(ioff[n] + 16) || !pin_out.reserve(ooff[n] + 16)) return CZ_E_MEM;
     for (size_t i = 0; i < n; i++) memcpy(pin_in.as<uint8_t>() + ioff[i], in_ptrs[i], in_lens[i]);
     int rc = inflate_batch_host(n, pin_in.as<uint8_t>(), ioff.data(), pin_out.as<uint8_t>(), ooff.data(), lens.data(), statuses,

@@ -5,7 +5,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -49,6 +51,38 @@ struct PinBuf {
 };
 
 inline uint64_t align_up(uint64_t v, uint64_t a) { return (v + a - 1) / a * a; }
+
+// Bounded per-device pool of reusable work objects (device / pinned buffers, streams). A call borrows one object for its
+// duration, so concurrent callers never share buffers, and at most KEEP idle objects per device outlive a call (a
+// 32-thread caller does not leave 32 sets of buffers behind; the reference's handles are one-thread-at-a-time but several
+// handles may run on several threads, SURVEY.md 8b "Threading").
+template <class T, int KEEP = 2>
+struct DevicePool {
+    std::mutex mu;
+    std::vector<T *> idle[64];
+    T *acquire(int dev) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            std::vector<T *> &v = idle[dev & 63];
+            if (!v.empty()) { T *w = v.back(); v.pop_back(); return w; }
+        }
+        return new (std::nothrow) T();
+    }
+    void release(int dev, T *w) {
+        if (!w) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            std::vector<T *> &v = idle[dev & 63];
+            if ((int)v.size() < KEEP) { v.push_back(w); return; }
+        }
+        delete w;
+    }
+};
+
+// kernels launched by this library since load (bench.py reports the count of the timed region as gpu_launches)
+void count_launches(unsigned k);
+bool profiling_on();  // cz_profile_enable (inflate.cu)
+#define CZ_KL(...) do { __VA_ARGS__; ::czh::count_launches(1); } while (0)
 
 // kernel launchers (defined in inflate.cu / deflate.cu)
 int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out,

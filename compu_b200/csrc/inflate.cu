@@ -32,7 +32,7 @@ static int launch_cfg(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams 
     uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
     if (ctas_needed < grid) grid = ctas_needed;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, W * 32, smem, st>>>(P);
+    CZ_KL(kern<<<(unsigned)grid, W * 32, smem, st>>>(P));
     return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
 }
 
@@ -53,7 +53,7 @@ static int launch_lane(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams
     uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
     if (ctas_needed < grid) grid = ctas_needed;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, W * 32, smem, st>>>(P);
+    CZ_KL(kern<<<(unsigned)grid, W * 32, smem, st>>>(P));
     return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
 }
 
@@ -74,7 +74,7 @@ static int launch_lc(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams &
     uint64_t grid = (uint64_t)ctx->sm_count * per_sm;
     if (ctas_needed < grid) grid = ctas_needed;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, W * 32, smem, st>>>(P);
+    CZ_KL(kern<<<(unsigned)grid, W * 32, smem, st>>>(P));
     return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
 }
 
@@ -87,7 +87,8 @@ uint64_t inflate_workspace_bytes(size_t n, uint64_t total_out_bytes) {
 }
 
 // Optional per-kernel timing of the two-phase path (bench.py: live CUDA-event durations of each kernel inside the timed region)
-static bool g_prof_on = false;
+static std::atomic<bool> g_prof_on{false};
+bool profiling_on() { return g_prof_on.load(std::memory_order_relaxed); }
 struct ProfRec { cudaEvent_t e0, e1, e2; };
 static std::vector<ProfRec> g_prof;
 static std::mutex g_prof_mu;
@@ -154,15 +155,15 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
             if (!CZ_CUDA(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l))) return CZ_E_MEM;
             conf_l[d] = true;
         }
-        kl<<<(unsigned)((P.n + 32 * WL - 1) / (32 * WL)), WL * 32, smem_l, st>>>(Q);
+        CZ_KL(kl<<<(unsigned)((P.n + 32 * WL - 1) / (32 * WL)), WL * 32, smem_l, st>>>(Q));
     } else
-    ka<<<(unsigned)ga, WA * 32, smem, st>>>(Q);
+    CZ_KL(ka<<<(unsigned)ga, WA * 32, smem, st>>>(Q));
     if (g_prof_on) cudaEventRecord(pr.e1, st);
     if (Q.cta_tile) {
         uint64_t gc = P.n, gcmax = (uint64_t)ctx->sm_count * per_sm_c[d];
         if (gc > gcmax) gc = gcmax;
-        if (g_lz_cta == 2) kc4<<<(unsigned)gc, 4 * 32, smem_c, st>>>(Q);
-        else kc<<<(unsigned)gc, WC * 32, smem_c, st>>>(Q);
+        if (g_lz_cta == 2) CZ_KL(kc4<<<(unsigned)gc, 4 * 32, smem_c, st>>>(Q));
+        else CZ_KL(kc<<<(unsigned)gc, WC * 32, smem_c, st>>>(Q));
     }
     uint64_t gb = (P.n + WB - 1) / WB;
     static int lz_cap = -1;  // experiment knob: CTAs of phase B per SM (fewer streams in flight => their windows fit L2)
@@ -177,11 +178,11 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
         if (!per_sm_w[d] && !CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_w[d], kw, 256, 0))) return CZ_E_MEM; \
         uint64_t gw = (P.n + 7) / 8, gwmax = (uint64_t)ctx->sm_count * (per_sm_w[d] > MINB ? MINB : per_sm_w[d]);  \
         if (gw > gwmax) gw = gwmax;                                                                                 \
-        kw<<<(unsigned)gw, 256, 0, st>>>(Q);                                                                        \
+        CZ_KL(kw<<<(unsigned)gw, 256, 0, st>>>(Q));                                                                        \
     } else
     CZ_LZW(3, 2, 12, 3) CZ_LZW(4, 2, 12, 2) CZ_LZW(5, 4, 8, 2) CZ_LZW(6, 2, 8, 4) CZ_LZW(7, 4, 8, 3)
 #undef CZ_LZW
-    kb<<<(unsigned)gb, WB * 32, 0, st>>>(Q);
+    CZ_KL(kb<<<(unsigned)gb, WB * 32, 0, st>>>(Q));
     if (g_prof_on) {
         cudaEventRecord(pr.e2, st);
         std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -190,6 +191,11 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
     return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
 }
 
+
+static int par_decode_off() {
+    static const int v = getenv("CZ_PAR_DECODE") ? 0 : 1;
+    return v;
+}
 
 // Counting mode: output size, status and consumed bytes of every unit, no output bytes (the speculative split's verify pass).
 // Runs the warp-per-stream kernel (a lone decoder lane per unit is ~6x faster per stream than the lane-per-stream kernels,
@@ -204,12 +210,13 @@ int launch_inflate_count(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_
     P.in = d_in; P.in_off = d_in_off; P.out = nullptr; P.out_off = d_out_off; P.out_lens = d_out_lens; P.statuses = d_statuses;
     P.in_consumed = d_in_consumed; P.checks = nullptr; P.counter = (unsigned long long *)d_ws; P.crc = ctx->d_crc;
     P.n = (uint32_t)n; P.ids = nullptr; P.window_bits = window_bits; P.segment_mode = segment_mode; P.check_kind = 0;
-    P.count_only = 1; P.serial_only = getenv("CZ_PAR_DECODE") ? 0 : 1;
+    P.count_only = 1; P.serial_only = par_decode_off();
     if (!CZ_CUDA(cudaMemsetAsync(d_ws, 0, 256, st))) return CZ_E_MEM;
     return launch_cfg<1, 8>(st, ctx, P);
 }
 
 static InflateCfg g_cfg = {0, 0};
+
 
 static InflateCfg pick_cfg() {
     if (g_cfg.D == 0) {
@@ -239,7 +246,7 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
     P.in_consumed = d_in_consumed; P.checks = d_checks; P.counter = (unsigned long long *)d_ws; P.crc = ctx->d_crc;
     P.n = (uint32_t)(d_ids ? n_ids : n); P.ids = d_ids;
     P.window_bits = window_bits; P.segment_mode = segment_mode; P.check_kind = check_kind; P.count_only = 0;
-    P.serial_only = getenv("CZ_PAR_DECODE") ? 0 : 1;
+    P.serial_only = par_decode_off();
     if (!CZ_CUDA(cudaMemsetAsync(d_ws, 0, 256, st))) return CZ_E_MEM;
     InflateCfg c = pick_cfg();
     // big units (one stream is megabytes): one WARP per stream, a single decoder lane feeding warp-cooperative LZ77 rounds —
@@ -322,7 +329,7 @@ extern "C" int cz_inflate_segments_device(void *cuda_stream, size_t n, const uin
                           nullptr, d_checks, -15, 1, d_checks ? 3 : 0, d_workspace, workspace_bytes, total_out_bytes, nullptr, 0, 0);
 }
 
-extern "C" void cz_profile_enable(int on) { g_prof_on = on != 0; }
+extern "C" void cz_profile_enable(int on) { g_prof_on.store(on != 0); }
 
 extern "C" int cz_profile_read(double *ms_decode, double *ms_resolve) {
     std::lock_guard<std::mutex> lk(g_prof_mu);

@@ -259,7 +259,10 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lane_kernel(InflateParams 
             ckmode = P.segment_mode ? (P.check_kind & 3) : wrap;
             if (wrap == 1) r = parse_zlib_header(br);
             else if (wrap == 2) r = parse_gzip_header(br);
-            if (r == 0) st = SS_BLOCK;
+            // an empty unit: one inflate() call with avail_in == 0 makes no progress — Z_BUF_ERROR, which compu's glue reports
+            // as NeedOutput (/root/reference/src/decoder/mod.rs:481)
+            if (in_len == 0 && !P.segment_mode) { result = ST_NEED_OUTPUT; st = SS_FINISH; }
+            else if (r == 0) st = SS_BLOCK;
             else { result = r == 100 ? ST_NEED_INPUT : r; st = SS_FINISH; }
         }
 

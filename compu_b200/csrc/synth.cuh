@@ -8,6 +8,11 @@
 // Integer arithmetic only (splitmix64 + table lookups), so the C, CUDA and emulated builds agree bit for bit.
 // A "unit" is an independently seeded piece: unit i covers out[offsets[i], offsets[i+1]) with seed base_seed + i.
 #pragma once
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
 #include "czk_common.cuh"
 
 namespace czk {
@@ -105,6 +110,46 @@ __host__ __device__ inline void synth_fill_unit(const SynthModel *m, int kind, u
     }
 }
 
+// Builds the model from a corpus (host): order-2 successor counts and the Zipf(1.2) table. Returns 0, or -4 when the corpus
+// has more distinct order-2 transitions than the table holds. `zipf_pow(r)` = r^-1.2 as a double (host libm).
+inline int synth_build_model(const uint8_t *corpus, uint64_t corpus_len, SynthModel *m) {
+    if (!corpus || corpus_len < 3 || !m) return -2;
+    memset(m, 0, sizeof *m);
+    std::vector<uint32_t> freq((size_t)65536 * 256, 0);
+    for (uint64_t i = 2; i < corpus_len; i++) {
+        uint32_t ctx = ((uint32_t)corpus[i - 2] << 8) | corpus[i - 1];
+        freq[(size_t)ctx * 256 + corpus[i]]++;
+    }
+    m->start_ctx = ((uint32_t)corpus[0] << 8) | corpus[1];
+    uint32_t n = 0;
+    for (uint32_t ctx = 0; ctx < 65536; ctx++) {
+        uint32_t cum = 0, cnt = 0, off = n;
+        for (uint32_t b = 0; b < 256; b++) {
+            uint32_t f = freq[(size_t)ctx * 256 + b];
+            if (!f) continue;
+            if (n >= CZK_SYNTH_MAX_ENTRIES) return -4;
+            cum += f;
+            m->entries[n++] = (cum << 8) | b;
+            cnt++;
+        }
+        m->ctx_index[ctx] = (off << 12) | cnt;
+        m->ctx_total[ctx] = cum;
+    }
+    m->n_entries = n;
+    // Zipf(1.2) over 4096 ranks: host doubles here, the kernels only see the integer table
+    double tot = 0;
+    for (uint32_t r = 1; r <= CZK_SYNTH_PHRASES; r++) tot += pow((double)r, -1.2);
+    double acc = 0;
+    for (uint32_t r = 1; r <= CZK_SYNTH_PHRASES; r++) {
+        acc += pow((double)r, -1.2);
+        double v = acc / tot * 4294967295.0;
+        m->zipf_cum[r - 1] = v >= 4294967295.0 ? 0xffffffffu : (uint32_t)v;
+    }
+    m->zipf_cum[CZK_SYNTH_PHRASES - 1] = 0xffffffffu;
+    return 0;
+}
+
+#if !defined(CZK_MODEL)
 __global__ void __launch_bounds__(128) synth_kernel(const SynthModel *m, int kind, uint64_t base_seed, uint32_t n, uint8_t *out,
                                                     const uint64_t *offsets) {
     uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
@@ -112,5 +157,6 @@ __global__ void __launch_bounds__(128) synth_kernel(const SynthModel *m, int kin
     uint64_t o0 = offsets[u], o1 = offsets[u + 1];
     synth_fill_unit(m, kind, base_seed, u, out + o0, o1 - o0, o0);
 }
+#endif
 
 }  // namespace czk

@@ -71,6 +71,10 @@ const char *cz_version(void);
 /* Text of the last CUDA/host failure on the calling thread ("" if none), static/thread storage. */
 const char *cz_last_error(void);
 
+/* Kernels launched by this library since it was loaded (all threads, all devices). bench.py reports the difference over
+   its timed region as "gpu_launches". */
+uint64_t cz_launch_count(void);
+
 /* Pinned (page-locked) host memory for zero-staging transfers; the pinned analogue of compu_malloc/compu_free. */
 void *cz_host_alloc(size_t bytes);
 void cz_host_free(void *p);
@@ -162,6 +166,9 @@ int cz_inflate_segments_device(void *cuda_stream, size_t n, const uint8_t *d_in,
    the last read, waits for them, and returns the number of launches. */
 void cz_profile_enable(int on);
 int cz_profile_read(double *ms_decode, double *ms_resolve);
+/* Same for the deflate kernel chain: summed durations (ms) of the match-search kernel(s) and of the whole chain of every
+   cz_deflate_* launch since the last read. */
+int cz_profile_read_deflate(double *ms_match, double *ms_chain);
 
 /* Deflate on device. Unit i = d_in[in_offsets[i]..in_offsets[i+1]) is compressed as ONE raw full-flush segment (no header,
    no BFINAL, ends byte-aligned with 00 00 ff ff) into d_out[out_offsets[i]..]; d_out_lens[i] = bytes written (or needed, with

@@ -21,6 +21,27 @@ def build(force=False):
     return _SO
 
 
+_synth = None
+
+
+def synth():
+    """oracle/libcompu_synth.so: the synthetic-data generator alone (host build of compu_b200/csrc/synth.cuh, no codec)."""
+    global _synth
+    if _synth is None:
+        so = os.path.join(_HERE, "libcompu_synth.so")
+        src = os.path.join(_HERE, "synth_host.cpp")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libcompu_synth.so"])
+        S = ctypes.CDLL(so)
+        S.oz_synth_model_bytes.restype = ctypes.c_uint64
+        S.oz_synth_build_model.restype = ctypes.c_int
+        S.oz_synth_build_model.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
+        S.oz_synth_fill.restype = ctypes.c_int
+        S.oz_synth_fill.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _synth = S
+    return _synth
+
+
 _lib = None
 
 

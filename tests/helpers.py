@@ -99,3 +99,128 @@ def assert_inflate_parity(outs, st, ref_outs, ref_st, tag=""):
         else:
             k = min(len(outs[i]), len(ref_outs[i]))
             assert outs[i][:k] == ref_outs[i][:k], "%s stream %d: partial output is not a prefix" % (tag, i)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# A small RFC 1951 reader used to LOOK INSIDE encoder output (block types, literal / match mix, distances) — the zlib module
+# only says whether a stream decodes. Pure Python, for inputs up to a few hundred KB.
+_LEN_BASE = [3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258]
+_LEN_EXTRA = [0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0]
+_DIST_BASE = [1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289,
+              16385, 24577]
+_DIST_EXTRA = [0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13]
+
+
+class _Bits:
+    def __init__(self, data):
+        self.v = int.from_bytes(data, "little")
+        self.pos = 0
+        self.nbits = 8 * len(data)
+
+    def get(self, n):
+        assert self.pos + n <= self.nbits, "inspector ran past the end of the stream"
+        r = (self.v >> self.pos) & ((1 << n) - 1)
+        self.pos += n
+        return r
+
+
+def _canon(lengths):
+    """code lengths -> {(length, code): symbol}"""
+    table, code = {}, 0
+    for ln in range(1, 16):
+        for sym, l in enumerate(lengths):
+            if l == ln:
+                table[(ln, code)] = sym
+                code += 1
+        code <<= 1
+    return table
+
+
+def _decode_sym(b, table):
+    code = 0
+    for ln in range(1, 16):
+        code = (code << 1) | b.get(1)
+        s = table.get((ln, code))
+        if s is not None:
+            return s
+    raise AssertionError("inspector: invalid Huffman code")
+
+
+def inspect_deflate(raw):
+    """Walks a raw-deflate stream (no container). Returns (blocks, out_len, end_byte) where every block is a dict
+    {type: 0|1|2, final, literals, matches, dists: set, min_len, max_len, stored_len}."""
+    b = _Bits(raw)
+    blocks, out_len = [], 0
+    while True:
+        final, typ = b.get(1), b.get(2)
+        blk = {"type": typ, "final": final, "literals": 0, "matches": 0, "dists": set(), "min_len": None, "max_len": None, "stored_len": 0}
+        if typ == 0:
+            b.pos = (b.pos + 7) & ~7
+            ln, nln = b.get(16), b.get(16)
+            assert ln ^ 0xffff == nln
+            b.pos += 8 * ln
+            blk["stored_len"] = ln
+            out_len += ln
+        else:
+            assert typ in (1, 2), "reserved block type"
+            if typ == 1:
+                lt = _canon([8] * 144 + [9] * 112 + [7] * 24 + [8] * 8)
+                dt = _canon([5] * 32)
+            else:
+                hlit, hdist, hclen = b.get(5) + 257, b.get(5) + 1, b.get(4) + 4
+                order = [16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15]
+                cl = [0] * 19
+                for i in range(hclen):
+                    cl[order[i]] = b.get(3)
+                ct = _canon(cl)
+                lens = []
+                while len(lens) < hlit + hdist:
+                    s = _decode_sym(b, ct)
+                    if s < 16:
+                        lens.append(s)
+                    elif s == 16:
+                        lens += [lens[-1]] * (3 + b.get(2))
+                    elif s == 17:
+                        lens += [0] * (3 + b.get(3))
+                    else:
+                        lens += [0] * (11 + b.get(7))
+                lt, dt = _canon(lens[:hlit]), _canon(lens[hlit:hlit + hdist])
+            while True:
+                s = _decode_sym(b, lt)
+                if s < 256:
+                    blk["literals"] += 1
+                    out_len += 1
+                elif s == 256:
+                    break
+                else:
+                    ln = _LEN_BASE[s - 257] + b.get(_LEN_EXTRA[s - 257])
+                    ds = _decode_sym(b, dt)
+                    dist = _DIST_BASE[ds] + b.get(_DIST_EXTRA[ds])
+                    blk["matches"] += 1
+                    blk["dists"].add(dist)
+                    blk["min_len"] = ln if blk["min_len"] is None else min(blk["min_len"], ln)
+                    blk["max_len"] = ln if blk["max_len"] is None else max(blk["max_len"], ln)
+                    out_len += ln
+        blocks.append(blk)
+        if final:
+            break
+    return blocks, out_len, (b.pos + 7) // 8
+
+
+def gzip_member(payload_raw, data, fextra=None, fname=None, fcomment=None, fhcrc=False, bad_hcrc=False, ftext=False):
+    """Hand-built RFC 1952 member around a raw-deflate payload, with any combination of optional header fields."""
+    flg = (1 if ftext else 0) | (2 if fhcrc else 0) | (4 if fextra is not None else 0) | (8 if fname is not None else 0) | \
+          (16 if fcomment is not None else 0)
+    h = bytes([0x1f, 0x8b, 8, flg, 0x12, 0x34, 0x56, 0x78, 0, 3])
+    if fextra is not None:
+        h += len(fextra).to_bytes(2, "little") + fextra
+    if fname is not None:
+        h += fname + b"\0"
+    if fcomment is not None:
+        h += fcomment + b"\0"
+    if fhcrc:
+        c = zlib.crc32(h) & 0xffff
+        if bad_hcrc:
+            c ^= 0x0101
+        h += c.to_bytes(2, "little")
+    return h + payload_raw + (zlib.crc32(data) & 0xffffffff).to_bytes(4, "little") + (len(data) & 0xffffffff).to_bytes(4, "little")

@@ -63,3 +63,21 @@ def test_device_generator_matches_host():
         torch.cuda.synchronize()
         ref = host_fill(kind, 99, n, unit, model)
         assert (d_out.cpu().numpy() == ref).all()
+
+
+def test_oracle_side_generator_is_bit_identical():
+    """oracle/libcompu_synth.so (what bench.py --impl reference uses, so that arm never loads the product library) produces
+    the bytes of the product's host generator for every class."""
+    import oracle
+    S = oracle.synth()
+    corpus = np.frombuffer(read_golden("alice29.txt"), dtype=np.uint8)
+    m2 = np.zeros(int(S.oz_synth_model_bytes()), dtype=np.uint8)
+    assert S.oz_synth_build_model(_p(corpus), len(corpus), _p(m2)) == 0
+    model = build_model()
+    assert (m2 == model).all()
+    for kind in (0, 1, 2, 3):
+        a = host_fill(kind, 77, 24, 65536, model)
+        offs = np.arange(25, dtype=np.uint64) * 65536
+        b = np.zeros(24 * 65536, dtype=np.uint8)
+        assert S.oz_synth_fill(kind, 77, 24, _p(b), _p(offs), _p(m2)) == 0
+        assert (a == b).all()
