@@ -12,6 +12,7 @@
 #include <algorithm>
 
 #include "host_common.h"
+#include "inflate_kernel.cuh"
 
 namespace czh {
 
@@ -661,26 +662,42 @@ extern "C" int cz_inflate_batch_ptrs(size_t n, const uint8_t *const *in_ptrs, co
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Streaming decoder. The GPU kernel is one-shot per stream, the contract is chunked in both directions
-// (tests/decoder.rs:34 hands a 1-byte output; tests/encoder.rs:149 feeds the input in 4 chunks). So the backend stages:
-// every byte of input is copied into a pinned staging buffer (the caller's slice is only borrowed for the call), the
-// stream staged so far is inflated on the device, the decoded prefix is held and drained over this and later calls.
-// Statuses follow the reference map: all input taken and stream not ended -> NeedInput; undelivered output ->
-// NeedOutput with output_remain == 0; stream end decoded and everything delivered -> Finished, with the bytes after
-// the end of the stream reported as input_remain.
+// Streaming decoder: zlib's inflate() contract, call for call (/root/reference/src/decoder/mod.rs:459-486).
+//
+// Every cz_decode that can make progress is ONE launch of the warp-per-stream kernel in resumable mode
+// (inflate_kernel.cuh, ResumeState): the unit is [staged tail | this call's input], the output slot is exactly the caller's
+// buffer, and the kernel stops where zlib's inflate() would return — out of input inside a header / a code / a stored run, or
+// with the slot full in the middle of a match — leaving in the state what zlib keeps in its inflate_state. So device work is
+// linear in the stream (nothing is ever decoded twice except a partial header or code), and what the decoder holds between
+// calls is bounded: the bytes of the partial header or code that ended the last call (a few bytes; a gzip header with
+// FEXTRA / FNAME can be longer), the 32 KiB history (on the device, in front of the next slot) and the state itself.
+// Statuses and remainders are zlib's: all input taken unless the output filled up first, in which case the bytes after the
+// last one whose bits were used go back to the caller (input_remain); no progress at all is Z_BUF_ERROR -> NeedOutput.
+// The caller's buffers are read and written by the copy engine directly (cudaMemcpyAsync on the caller's pointers: zero
+// staging copies of ours when they are cz_host_alloc'ed / pinned; the driver stages pageable memory itself).
+// A stream that arrives whole in one call and is large takes the batched path first (speculative split, see above).
 struct DecoderState {
-    int window_bits;
-    int dev;
-    PinBuf in;            // staged compressed bytes
-    size_t in_len = 0;
-    PinBuf out;           // decoded bytes (prefix of the stream's output)
-    size_t out_len = 0;   // valid bytes in `out`
-    size_t delivered = 0; // bytes already handed to the caller
-    size_t out_cap_hint = 0;
-    bool dirty = false;   // new input since the last device pass
-    bool done = false;    // stream end decoded
-    int32_t error = 0;    // sticky error code (<0, or 3 = need dictionary)
-    size_t stream_bytes = 0;  // compressed length of the stream once done
+    int window_bits = 0;
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf d_in, d_out, d_meta;
+    PinBuf h_meta;                 // pinned: [ResumeState | in_off[2] | out_off[2] | out_len | status] up and down
+    std::vector<uint8_t> carry;    // staged tail: bytes from the one that holds rs.bit_pos on
+    czk::ResumeState rs;
+    uint64_t wpos = 0;             // d_out[wpos - rs.hist_len, wpos) is the history, the next slot starts at wpos
+    bool done = false;
+    int32_t error = 0;             // sticky (<0, or 3 = need dictionary)
+    void reset_stream() {
+        memset(&rs, 0, sizeof rs);
+        rs.adler = 1;
+        carry.clear();
+        wpos = 0;
+        done = false;
+        error = 0;
+    }
+    ~DecoderState() {
+        if (stream) { cudaSetDevice(dev); cudaStreamDestroy(stream); }
+    }
 };
 
 extern "C" void *cz_decoder_new(int window_bits) {
@@ -697,46 +714,89 @@ extern "C" void *cz_decoder_new(int window_bits) {
     if (!s) return nullptr;
     s->window_bits = window_bits;
     s->dev = dev;
+    s->reset_stream();
     return s;
 }
 
 extern "C" void *cz_decoder_reset(void *state) {
     DecoderState *s = (DecoderState *)state;
     if (!s) return nullptr;
-    s->in_len = s->out_len = s->delivered = 0;  // keeps the pinned allocations (cheap reset)
-    s->dirty = s->done = false;
-    s->error = 0;
-    s->stream_bytes = 0;
+    s->reset_stream();  // keeps the stream and the device / pinned allocations (cheap reset)
     return s;
 }
 
 extern "C" void cz_decoder_free(void *state) { delete (DecoderState *)state; }
 
-static int decoder_pass(DecoderState *s) {
-    // inflate everything staged so far as one unit; grow the output buffer until the slot is large enough
-    size_t cap = std::max<size_t>(s->out_cap_hint, std::max<size_t>(s->in_len * 4, 1 << 16));
-    if (s->window_bits > 15 && s->in_len >= 18) {
-        // gzip ISIZE (mod 2^32) is a cheap hint when the whole member is present
-        const uint8_t *t = s->in.as<uint8_t>() + s->in_len - 4;
-        size_t isz = (size_t)t[0] | (size_t)t[1] << 8 | (size_t)t[2] << 16 | (size_t)t[3] << 24;
-        if (isz > cap && isz < ((size_t)1 << 31)) cap = isz;
+static const uint32_t kWindow = 32768;
+
+// One resumable launch: decodes [carry | in) into out[0, out_len). Returns 0 and the kernel's verdict, or a CZ_E_* code.
+static int decoder_launch(DecoderState *s, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len, uint64_t *produced,
+                          int32_t *kstatus) {
+    DeviceCtx *ctx = device_ctx(s->dev);
+    if (!ctx) return CZ_E_NO_DEVICE;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    struct Restore { int d; ~Restore() { cudaSetDevice(d); } } restore{prev};
+    if (!CZ_CUDA(cudaSetDevice(s->dev))) return CZ_E_MEM;
+    if (!s->stream && !CZ_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking))) return CZ_E_MEM;
+    cudaStream_t st = s->stream;
+    const size_t nc = s->carry.size(), unit = nc + in_len;
+    // meta (device): [ResumeState 384 | in_off 16 | out_off 16 | out_len 8 | status 8 | pad -> 512 | counter 256]
+    const size_t m_rs = 0, m_ioff = sizeof(czk::ResumeState), m_ooff = m_ioff + 16, m_len = m_ooff + 16, m_stat = m_len + 8, m_cnt = 512,
+                 m_total = 768;
+    static_assert(sizeof(czk::ResumeState) + 48 <= 512, "meta layout");
+    if (!s->d_meta.reserve(m_total) || !s->h_meta.reserve(m_total + 512) || !s->d_in.reserve(unit + 64)) return CZ_E_MEM;
+    // output ring: history directly in front of the slot. When the slot does not fit behind the cursor, the history moves to
+    // the front (through a bounce area at the end of the buffer when the two ranges would overlap).
+    const uint32_t hist = s->rs.hist_len;
+    if (s->wpos + out_len + 16 > s->d_out.cap || s->wpos < hist) {
+        const size_t need = (size_t)kWindow * 3 + out_len + 64;  // (the bounce area at the end stays clear of cursor + slot)
+        if (need > s->d_out.cap) {
+            DevBuf nb;
+            if (!nb.reserve(need + (need >> 1))) return CZ_E_MEM;
+            if (hist && !CZ_CUDA(cudaMemcpyAsync(nb.p, s->d_out.as<uint8_t>() + s->wpos - hist, hist, cudaMemcpyDeviceToDevice, st))) return CZ_E_MEM;
+            if (!CZ_CUDA(cudaStreamSynchronize(st))) return CZ_E_MEM;
+            std::swap(nb.p, s->d_out.p);
+            std::swap(nb.cap, s->d_out.cap);
+        } else if (hist) {
+            uint8_t *base = s->d_out.as<uint8_t>();
+            if (s->wpos - hist >= hist) {
+                if (!CZ_CUDA(cudaMemcpyAsync(base, base + s->wpos - hist, hist, cudaMemcpyDeviceToDevice, st))) return CZ_E_MEM;
+            } else {  // ranges overlap: bounce through the last 32 KiB of the buffer (beyond any slot in use: cap >= 2 W + ...)
+                uint8_t *bounce = base + s->d_out.cap - kWindow;
+                if (!CZ_CUDA(cudaMemcpyAsync(bounce, base + s->wpos - hist, hist, cudaMemcpyDeviceToDevice, st)) ||
+                    !CZ_CUDA(cudaMemcpyAsync(base, bounce, hist, cudaMemcpyDeviceToDevice, st))) return CZ_E_MEM;
+            }
+        }
+        s->wpos = hist;
     }
-    for (;;) {
-        if (!s->out.reserve(cap + 16)) return CZ_E_MEM;
-        uint64_t in_off[2] = {0, s->in_len}, out_off[2] = {0, cap}, out_len = 0, consumed = 0;
-        int32_t status = 0;
-        int rc = inflate_batch_host(1, s->in.as<uint8_t>(), in_off, s->out.as<uint8_t>(), out_off, &out_len, &status, &consumed,
-                                    s->window_bits, 0, nullptr, 1u << s->dev);
-        if (rc) return rc;
-        // A full slot means "grow and retry" whatever the status says: when the symbol that did not fit ends in the last staged
-        // byte the kernels report NeedInput, as zlib would (avail_in == 0), but here the slot size is our own guess
-        if (status == CZ_DECODE_NEED_OUTPUT || (status == CZ_DECODE_NEED_INPUT && out_len >= cap)) { cap *= 2; continue; }
-        s->out_len = (size_t)out_len;
-        s->out_cap_hint = cap;
-        if (status == CZ_DECODE_FINISHED) { s->done = true; s->stream_bytes = (size_t)consumed; }
-        else if (status != CZ_DECODE_NEED_INPUT) s->error = status;
-        return 0;
+    uint8_t *hm = s->h_meta.as<uint8_t>();
+    memcpy(hm + m_rs, &s->rs, sizeof s->rs);
+    uint64_t *ioff = (uint64_t *)(hm + m_ioff), *ooff = (uint64_t *)(hm + m_ooff);
+    ioff[0] = 0; ioff[1] = unit; ooff[0] = 0; ooff[1] = out_len;
+    uint8_t *dm = s->d_meta.as<uint8_t>();
+    if (!CZ_CUDA(cudaMemcpyAsync(dm, hm, m_len, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
+    if (nc) {
+        memcpy(hm + m_total, s->carry.data(), nc <= 512 ? nc : 0);
+        const void *src = nc <= 512 ? (const void *)(hm + m_total) : (const void *)s->carry.data();
+        if (!CZ_CUDA(cudaMemcpyAsync(s->d_in.p, src, nc, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
     }
+    if (in_len && !CZ_CUDA(cudaMemcpyAsync(s->d_in.as<uint8_t>() + nc, in, in_len, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
+    int rc = launch_inflate_resume(st, ctx, s->d_in.as<uint8_t>(), (const uint64_t *)(dm + m_ioff), s->d_out.as<uint8_t>() + s->wpos,
+                                   (const uint64_t *)(dm + m_ooff), (uint64_t *)(dm + m_len), (int32_t *)(dm + m_stat), s->window_bits,
+                                   (czk::ResumeState *)(dm + m_rs), dm + m_cnt);
+    if (rc) return rc;
+    if (!CZ_CUDA(cudaMemcpyAsync(hm, dm, m_stat + 8, cudaMemcpyDeviceToHost, st)) || !CZ_CUDA(cudaStreamSynchronize(st))) return CZ_E_MEM;
+    memcpy(&s->rs, hm + m_rs, sizeof s->rs);
+    *produced = *(const uint64_t *)(hm + m_len);
+    *kstatus = *(const int32_t *)(hm + m_stat);
+    if (*produced > out_len) { set_error("internal: resumable launch overran its slot"); return CZ_E_MEM; }
+    if (*produced) {
+        if (!CZ_CUDA(cudaMemcpyAsync(out, s->d_out.as<uint8_t>() + s->wpos, *produced, cudaMemcpyDeviceToHost, st)) ||
+            !CZ_CUDA(cudaStreamSynchronize(st))) return CZ_E_MEM;
+        s->wpos += *produced;
+    }
+    return 0;
 }
 
 extern "C" cz_result cz_decode(void *state, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len) {
@@ -745,34 +805,59 @@ extern "C" cz_result cz_decode(void *state, const uint8_t *in, size_t in_len, ui
     r.input_remain = in_len;
     r.output_remain = out_len;
     if (!s) { r.status = CZ_E_STREAM; return r; }
-    if (s->error) { r.status = s->error == 3 ? 3 : s->error; return r; }
-    if (!s->done && in_len) {
-        if (!s->in.reserve(s->in_len + in_len + 16, true, s->in_len)) { r.status = CZ_E_MEM; return r; }
-        memcpy(s->in.as<uint8_t>() + s->in_len, in, in_len);
-        s->in_len += in_len;
-        s->dirty = true;
-        r.input_remain = 0;
-    }
-    if (s->dirty) {
-        s->dirty = false;
-        int rc = decoder_pass(s);
-        if (rc) { s->error = rc; r.status = rc; return r; }
-        if (s->done) {
-            // bytes staged beyond the end of the stream belong to the caller: they all come from this call
-            size_t extra = s->in_len - s->stream_bytes;
-            r.input_remain = extra <= in_len ? extra : in_len;
-            s->in_len = s->stream_bytes;
+    if (s->error) { r.status = s->error; return r; }         // zlib: mode BAD stays BAD
+    if (s->done) { r.status = CZ_DECODE_FINISHED; return r; }  // zlib: mode DONE returns Z_STREAM_END again, nothing consumed
+    // a large stream that arrives whole at the very start: the batched path (speculative split at verified full-flush points)
+    static const bool no_split = getenv("CZ_NO_SPLIT") != nullptr;
+    const bool fresh = s->rs.phase == czk::RP_HEADER && s->rs.total_out == 0 && s->carry.empty();
+    if (fresh && !no_split && in_len >= huge_unit_bytes()) {
+        uint64_t got = 0, used = 0;
+        int32_t st = 0;
+        g_split_tried++;
+        if (inflate_split_speculative(in, in_len, out, out_len, s->window_bits, 1u << s->dev, &got, &st, &used) &&
+            (st == CZ_DECODE_FINISHED || st == CZ_E_DATA)) {
+            g_split_ok++;
+            r.output_remain = out_len - (size_t)got;
+            if (st == CZ_DECODE_FINISHED) { s->done = true; r.input_remain = in_len - (size_t)used; }
+            else s->error = st;
+            r.status = st;
+            return r;
         }
     }
-    size_t avail = s->out_len - s->delivered;
-    size_t k = avail < out_len ? avail : out_len;
-    if (k) memcpy(out, s->out.as<uint8_t>() + s->delivered, k);
-    s->delivered += k;
-    r.output_remain = out_len - k;
-    if (s->delivered < s->out_len) r.status = CZ_DECODE_NEED_OUTPUT;
-    else if (s->error) r.status = s->error;  // everything decoded before the error has been delivered
-    else if (s->done) r.status = CZ_DECODE_FINISHED;
-    else if (in_len == 0 && k == 0) r.status = CZ_DECODE_NEED_OUTPUT;  // no progress possible: zlib's Z_BUF_ERROR -> NeedOutput (mod.rs:481)
-    else r.status = CZ_DECODE_NEED_INPUT;
+    uint64_t produced = 0;
+    int32_t ks = 0;
+    int rc = decoder_launch(s, in, in_len, out, out_len, &produced, &ks);
+    if (rc) { s->error = rc; r.status = rc; return r; }
+    const size_t nc = s->carry.size(), unit = nc + in_len;
+    const uint64_t B = s->rs.bit_pos;
+    r.output_remain = out_len - (size_t)produced;
+    if (ks == CZ_DECODE_FINISHED) {
+        s->done = true;
+        const uint64_t used = (B + 7) >> 3;               // the trailer ends on a byte boundary
+        r.input_remain = unit > used ? (size_t)(unit - used) : 0;  // bytes after the end of the stream belong to the caller
+        if (r.input_remain > in_len) r.input_remain = in_len;
+        s->carry.clear();
+        r.status = CZ_DECODE_FINISHED;
+        return r;
+    }
+    if (ks < 0 || ks == CZ_DECODE_NEED_DICT) {  // everything decoded before the error has been written (as zlib does)
+        s->error = ks;
+        r.input_remain = 0;
+        r.status = ks;
+        return r;
+    }
+    // Z_OK: rebuild the staged tail from the byte that holds the next bit
+    std::vector<uint8_t> tail;
+    size_t keep_from = (size_t)(B >> 3), keep_to;
+    if (ks == CZ_DECODE_NEED_INPUT) { keep_to = unit; r.input_remain = 0; }        // everything is taken; the partial item stays staged
+    else { keep_to = (size_t)((B + 7) >> 3); r.input_remain = unit - keep_to; }  // slot full: only the byte in use stays
+    if (r.input_remain > in_len) { set_error("internal: resumable decoder gave back more than it was given"); s->error = CZ_E_MEM; r.status = CZ_E_MEM; return r; }
+    tail.reserve(keep_to > keep_from ? keep_to - keep_from : 0);
+    for (size_t k = keep_from; k < keep_to; k++) tail.push_back(k < nc ? s->carry[k] : in[k - nc]);
+    s->carry.swap(tail);
+    s->rs.bit_pos = B & 7;
+    const size_t used_in = in_len - r.input_remain;
+    if (r.input_remain == 0 && !(used_in == 0 && produced == 0)) r.status = CZ_DECODE_NEED_INPUT;
+    else r.status = CZ_DECODE_NEED_OUTPUT;  // output full — or no progress at all: Z_BUF_ERROR -> NeedOutput (mod.rs:481)
     return r;
 }

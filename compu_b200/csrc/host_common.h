@@ -94,6 +94,13 @@ int launch_inflate_count(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_
                          const uint64_t *d_out_off, uint64_t *d_out_lens, int32_t *d_statuses, uint64_t *d_in_consumed,
                          int window_bits, int segment_mode, void *d_ws, uint64_t ws_bytes);
 
+}  // namespace czh
+namespace czk { struct ResumeState; }
+namespace czh {
+int launch_inflate_resume(cudaStream_t st, DeviceCtx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out,
+                          const uint64_t *d_out_off, uint64_t *d_out_lens, int32_t *d_statuses, int window_bits,
+                          czk::ResumeState *d_resume, void *d_ws);
+
 // batched inflate over host memory (host.cu); segment_mode / checks as in cz_inflate_segments_device
 int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint8_t *out, const uint64_t *out_off,
                        uint64_t *out_lens, int32_t *statuses, uint64_t *in_consumed, int window_bits, int segment_mode,

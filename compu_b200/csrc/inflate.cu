@@ -215,6 +215,19 @@ int launch_inflate_count(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_
     return launch_cfg<1, 8>(st, ctx, P);
 }
 
+// One resumable unit (the streaming Decoder): the warp-per-stream kernel with its ResumeState. d_ws: 256 bytes.
+int launch_inflate_resume(cudaStream_t st, DeviceCtx *ctx, const uint8_t *d_in, const uint64_t *d_in_off, uint8_t *d_out,
+                          const uint64_t *d_out_off, uint64_t *d_out_lens, int32_t *d_statuses, int window_bits,
+                          czk::ResumeState *d_resume, void *d_ws) {
+    czk::InflateParams P;
+    memset(&P, 0, sizeof P);
+    P.in = d_in; P.in_off = d_in_off; P.out = d_out; P.out_off = d_out_off; P.out_lens = d_out_lens; P.statuses = d_statuses;
+    P.counter = (unsigned long long *)d_ws; P.crc = ctx->d_crc; P.n = 1; P.window_bits = window_bits; P.serial_only = 1;
+    P.resume = d_resume;
+    if (!CZ_CUDA(cudaMemsetAsync(d_ws, 0, 256, st))) return CZ_E_MEM;
+    return launch_cfg<1, 8>(st, ctx, P);
+}
+
 static InflateCfg g_cfg = {0, 0};
 
 
@@ -247,6 +260,7 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
     P.n = (uint32_t)(d_ids ? n_ids : n); P.ids = d_ids;
     P.window_bits = window_bits; P.segment_mode = segment_mode; P.check_kind = check_kind; P.count_only = 0;
     P.serial_only = par_decode_off();
+    P.resume = nullptr;
     if (!CZ_CUDA(cudaMemsetAsync(d_ws, 0, 256, st))) return CZ_E_MEM;
     InflateCfg c = pick_cfg();
     // big units (one stream is megabytes): one WARP per stream, a single decoder lane feeding warp-cooperative LZ77 rounds —

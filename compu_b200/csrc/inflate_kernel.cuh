@@ -32,6 +32,35 @@ namespace czk {
 #endif
 #define CZK_TOKENS 32
 
+// Resumable decoding of ONE long-lived stream (the streaming Decoder, cz_decode): a unit may stop anywhere zlib's inflate()
+// may return — out of input in the middle of a header, a code or a stored run; output slot full in the middle of a match —
+// and the next launch picks up exactly there. What carries over is what zlib keeps in its inflate_state: the bit position, the
+// current block's code lengths, a token that did not fit yet, the running check values, and the last 32 KiB of output (which the
+// host keeps right in front of the unit's output slot).
+enum ResumePhase : uint32_t {
+    RP_HEADER = 0,   // container header not parsed yet (restart at bit_pos; the header is re-read whole)
+    RP_BLOCK = 1,    // a block header comes next
+    RP_CODES = 2,    // inside a fixed / dynamic block: lens[] holds its code lengths
+    RP_STORED = 3,   // inside a stored block: stored_left bytes still to copy
+    RP_TRAILER = 4,  // all blocks done, the container trailer comes next
+    RP_DONE = 5
+};
+struct ResumeState {
+    uint64_t bit_pos;     // in: where decoding restarts, in bits from the start of the unit's input; out: where to restart next
+    uint64_t total_out;   // bytes produced by earlier launches (ISIZE check)
+    uint32_t phase;       // ResumePhase
+    uint32_t bfinal;      // BFINAL of the current block
+    uint32_t nlit, ndist; // RP_CODES: alphabet sizes of lens[]
+    uint32_t stored_left; // RP_STORED
+    uint32_t wrap;        // container kind once the header has been parsed (0 raw, 1 zlib, 2 gzip)
+    uint32_t hist_len;    // valid history bytes right in front of the output slot (<= 32768)
+    uint32_t adler, crc;  // running check values over everything produced so far
+    uint32_t pend_len;    // != 0: a decoded token that has not been (completely) written: pend_len bytes still to produce ...
+    uint32_t pend_dist;   // ... by copying from pend_dist back (a match), or, with pend_dist == 0, the literal byte pend_lit
+    uint32_t pend_lit;
+    uint8_t lens[320];
+};
+
 struct InflateParams {
     const uint8_t *in;
     const uint64_t *in_off;   // n+1
@@ -50,6 +79,7 @@ struct InflateParams {
     int32_t check_kind;       // segment_mode only: bit0 adler, bit1 crc into `checks`
     int32_t count_only;       // inflate_kernel only: produce no output bytes, just sizes / statuses / consumed (out may be null)
     int32_t serial_only;      // inflate_kernel<1, W> only: 1 = no speculative decode by the idle lanes (experiments)
+    ResumeState *resume;      // inflate_kernel only, optional: per-unit resume state (in/out), see ResumeState
 };
 
 // litlen table entry (u16): bits 0-3 code length, bits 4-15 payload
@@ -71,8 +101,8 @@ struct SlotSmem {
     uint16_t lit_first[16], lit_offs[16], lit_count[16];
     uint16_t dist_first[16], dist_offs[16], dist_count[16];
     uint8_t dist_sorted[32];
-    union {
-        uint8_t lens[320];            // code lengths while a block header is parsed / tables are built
+    struct {
+        uint8_t lens[320];            // code lengths of the current block (kept: a resumable unit hands them to its next launch)
         uint32_t tokens[CZK_TOKENS];  // token queue while the block is decoded
     } u;
     uint32_t cnt[16];
@@ -479,6 +509,11 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
     uint32_t bfinal = 0, ntok = 0, nlit = 0, ndist = 0, stored_len = 0;
     int after_tokens = SS_DECODE;  // state to enter once the token queue has been drained
     int full_status = -1;          // >= 0: the decoder stopped at the first token that does not fit the slot; its status
+    // resumable units (P.resume): where and in which phase the next launch restarts, history in front of the slot, bytes of
+    // earlier launches, and a decoded token that did not fit (completely) yet
+    uint64_t rbits = 0, prior_out = 0;
+    uint32_t rphase = RP_HEADER, hist = 0, pend_len = 0, pend_dist = 0, pend_lit = 0;
+    const bool resumable = P.resume != nullptr;
     SlotSmem &my = slots[lane < D ? lane : 0];
 
     for (;;) {
@@ -494,6 +529,22 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 adler = 1; crc = 0; ntok = 0; bfinal = 0; result = 0; full_status = -1;
                 br.init(in_base, in_len);
                 st = SS_HEADER;
+                if (resumable) {
+                    const ResumeState &R = P.resume[unit];
+                    hist = R.hist_len; prior_out = R.total_out; adler = R.adler; crc = R.crc; bfinal = R.bfinal; wrap = (int)R.wrap;
+                    pend_len = R.pend_len; pend_dist = R.pend_dist; pend_lit = R.pend_lit;
+                    rbits = R.bit_pos; rphase = R.phase;
+                    br.seek(rbits >> 3);
+                    br.skip((uint32_t)(rbits & 7));
+                    if (rphase == RP_BLOCK) st = SS_BLOCK;
+                    else if (rphase == RP_CODES) {
+                        nlit = R.nlit; ndist = R.ndist;
+                        for (uint32_t i = 0; i < nlit + ndist && i < 320; i++) my.u.lens[i] = R.lens[i];
+                        st = SS_BUILD;
+                    } else if (rphase == RP_STORED) { stored_len = R.stored_left; st = SS_STORED; }
+                    else if (rphase == RP_TRAILER) { result = ST_FINISHED; st = SS_TRAILER; }
+                    else if (rphase == RP_DONE) { result = ST_FINISHED; st = SS_FINISH; }
+                }
             }
         }
         if (__all_sync(CZK_FULL, st == SS_EXIT)) break;
@@ -523,6 +574,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 result = br.consumed() == br.total ? ST_FINISHED : ST_NEED_INPUT;
                 st = SS_TRAILER;
             } else {
+                if (resumable) { rphase = RP_BLOCK; rbits = br.consumed(); }  // out of input inside the header: back to its start
                 br.refill();
                 bfinal = br.get(1);
                 uint32_t btype = br.get(2);
@@ -566,7 +618,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 __syncwarp();
                 if ((int)lane == s) {
                     if (r || r2) { result = ST_E_DATA; st = SS_FINISH; }
-                    else { st = SS_DECODE; ntok = 0; }
+                    else { st = SS_DECODE; ntok = 0; rphase = RP_CODES; }
                 }
             }
         }
@@ -582,7 +634,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
         // compaction) is ~35 dependent instructions per token against ~50 for the serial lane. OFF by default (CZ_PAR_DECODE=1).
         bool par_eob = false;
         if constexpr (D == 1) {
-            const bool can = !P.serial_only && __shfl_sync(CZK_FULL, (int)(st == SS_DECODE), 0) != 0;
+            const bool can = !P.serial_only && !resumable && __shfl_sync(CZK_FULL, (int)(st == SS_DECODE), 0) != 0;
             if (can) {
                 const uint8_t *ib0 = (const uint8_t *)(uintptr_t)__shfl_sync(CZK_FULL, (unsigned long long)(uintptr_t)in_base, 0);
                 uint64_t cpos = __shfl_sync(CZK_FULL, (unsigned long long)br.consumed(), 0);
@@ -669,7 +721,14 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
             // the queue must not run ahead of it (the status and the consumed-byte count depend on where it stops)
             uint64_t room = out_cap - out_pos;
             const bool track = ntok == 0;  // (tokens queued by the speculative path (5p) are not accounted for)
-            while (ntok < CZK_TOKENS) {
+            bool stop = false;
+            if (resumable && pend_len) {  // the token the previous launch could not finish comes first
+                const uint32_t n = pend_len < room ? pend_len : (uint32_t)room;
+                if (n) { tok[ntok++] = pend_dist ? ((pend_dist << 9) | n) : (0x80000000u | (pend_lit << 9) | 1u); room -= n; pend_len -= n; }
+                if (pend_len) { result = ST_NEED_OUTPUT; after_tokens = SS_FINISH; stop = true; }
+            }
+            while (!stop && ntok < CZK_TOKENS) {
+                if (resumable) rbits = br.consumed();  // out of input inside this symbol: the next launch re-reads it
                 br.refill();
                 uint32_t e = my.lit_tab[br.peek(CZK_LIT_BITS)];
                 if ((e & 0xfff0u) == CZK_L_LONG) e = decode_long_lit(my, br.peek(15));
@@ -677,6 +736,13 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 if (pay < 0x100) {  // literal
                     br.skip(e & 15);
                     if (br.overrun()) { result = ST_NEED_INPUT; after_tokens = SS_FINISH; break; }
+                    if (resumable) {
+                        // zlib has taken the symbol's bits when it finds no room for its byte (inflate.c LIT): so does the state
+                        if (room == 0) { pend_len = 1; pend_dist = 0; pend_lit = pay; rbits = br.consumed(); result = ST_NEED_OUTPUT; after_tokens = SS_FINISH; break; }
+                        room--;
+                        tok[ntok++] = 0x80000000u | (pay << 9) | 1u;
+                        continue;
+                    }
                     tok[ntok++] = 0x80000000u | (pay << 9) | 1u;
                     if (track) {
                         if (room == 0) { full_status = br.out_full_status(); after_tokens = SS_FINISH; break; }
@@ -715,6 +781,14 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 uint32_t dist = (((de >> 8) & 3) << deb) + 1 + br.peek(deb);
                 br.skip(deb);
                 if (br.overrun()) { result = ST_NEED_INPUT; after_tokens = SS_FINISH; break; }
+                if (resumable) {
+                    // the part of the match that fits is written, the rest waits in the state (inflate.c MATCH: state->length)
+                    const uint32_t n = len < room ? len : (uint32_t)room;
+                    if (n) tok[ntok++] = (dist << 9) | n;
+                    room -= n;
+                    if (n < len) { pend_len = len - n; pend_dist = dist; rbits = br.consumed(); result = ST_NEED_OUTPUT; after_tokens = SS_FINISH; break; }
+                    continue;
+                }
                 tok[ntok++] = (dist << 9) | len;
                 if (track) {
                     if (len > room) { full_status = br.out_full_status(); after_tokens = SS_FINISH; break; }
@@ -734,6 +808,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 uint8_t *ob = (uint8_t *)(uintptr_t)__shfl_sync(CZK_FULL, (unsigned long long)(uintptr_t)out_base, s);
                 const uint64_t opos = __shfl_sync(CZK_FULL, (unsigned long long)out_pos, s);
                 const uint64_t ocap = __shfl_sync(CZK_FULL, (unsigned long long)out_cap, s);
+                const uint32_t hist_s = __shfl_sync(CZK_FULL, hist, s);
                 __syncwarp();
                 uint32_t t = lane < nt ? slots[s].u.tokens[lane] : 0;
                 uint32_t tl = t & 0x1ff;
@@ -746,7 +821,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 uint32_t total = __shfl_sync(CZK_FULL, pos, 31);
                 pos -= tl;
                 // distance validity: dist <= bytes produced before the token ("invalid distance too far back")
-                bool bad = lane < nt && !(t >> 31) && (uint64_t)(t >> 9) > opos + pos;
+                bool bad = lane < nt && !(t >> 31) && (uint64_t)(t >> 9) > opos + pos + hist_s;
                 uint32_t badm = __ballot_sync(CZK_FULL, bad);
                 int err = 0;
                 if (badm) {
@@ -829,7 +904,10 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
                 __syncwarp();
                 if ((int)lane == s) {
                     out_pos = opos + n;
-                    if (err >= 0) { result = err; st = SS_FINISH; br.seek(ipos + n); }
+                    if (err >= 0) {
+                        result = err; st = SS_FINISH; br.seek(ipos + n);
+                        if (resumable) { rphase = RP_STORED; rbits = (ipos + n) * 8; stored_len = len - n; }
+                    }
                     else {
                         br.seek(ipos + n);
                         if (bfinal) { result = ST_FINISHED; st = SS_TRAILER; } else st = SS_BLOCK;
@@ -891,18 +969,23 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
             if (!P.segment_mode && result == ST_FINISHED) {
                 // back to a byte boundary, then the container trailer
                 br.skip((uint32_t)((0 - br.consumed()) & 7));
+                if (resumable) { rphase = RP_TRAILER; rbits = br.consumed(); }
                 if (wrap == 1) {
                     uint32_t v = 0;
                     for (int i = 0; i < 4; i++) v = (v << 8) | br.get_byte();
                     if (br.overrun()) result = ST_NEED_INPUT;
                     else if (v != adler) result = ST_E_DATA;  // "incorrect data check"
                 } else if (wrap == 2) {
+                    // zlib judges the CRC as soon as its four bytes are there (inflate.c CHECK), before it asks for ISIZE
                     uint32_t v = 0, isz = 0;
                     for (int i = 0; i < 4; i++) v |= br.get_byte() << (8 * i);
-                    for (int i = 0; i < 4; i++) isz |= br.get_byte() << (8 * i);
                     if (br.overrun()) result = ST_NEED_INPUT;
                     else if (v != crc) result = ST_E_DATA;                 // "incorrect data check"
-                    else if (isz != (uint32_t)out_pos) result = ST_E_DATA;  // "incorrect length check"
+                    else {
+                        for (int i = 0; i < 4; i++) isz |= br.get_byte() << (8 * i);
+                        if (br.overrun()) result = ST_NEED_INPUT;
+                        else if (isz != (uint32_t)(prior_out + out_pos)) result = ST_E_DATA;  // "incorrect length check"
+                    }
                 }
             }
             st = SS_FINISH;
@@ -910,6 +993,19 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
 
         // ---- (10) report
         if (st == SS_FINISH) {
+            if (resumable) {
+                ResumeState &R = P.resume[unit];
+                R.bit_pos = result == ST_FINISHED ? br.consumed() : rbits;
+                R.phase = result == ST_FINISHED ? (uint32_t)RP_DONE : rphase;
+                R.total_out = prior_out + out_pos;
+                R.bfinal = bfinal; R.nlit = nlit; R.ndist = ndist; R.stored_left = stored_len; R.wrap = (uint32_t)wrap;
+                const uint64_t h = (uint64_t)hist + out_pos;
+                R.hist_len = h > 32768 ? 32768u : (uint32_t)h;
+                R.adler = adler; R.crc = crc;
+                R.pend_len = pend_len; R.pend_dist = pend_dist; R.pend_lit = pend_lit;
+                if (rphase == RP_CODES)
+                    for (uint32_t i = 0; i < nlit + ndist && i < 320; i++) R.lens[i] = my.u.lens[i];
+            }
             P.out_lens[unit] = out_pos;
             P.statuses[unit] = result;
             if (P.in_consumed) {

@@ -289,12 +289,17 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
                     if (br.overrun()) result = ST_NEED_INPUT;
                     expect = t;
                 } else if (wrap == 2) {
+                    // zlib judges the CRC as soon as its four bytes are there (inflate.c CHECK), before it asks for ISIZE: a unit
+                    // cut inside ISIZE is a data error if the CRC is wrong, NeedInput otherwise — phase B decides (wrap bit 2)
                     uint32_t t = 0, isz = 0;
                     for (int i = 0; i < 4; i++) t |= br.get_byte() << (8 * i);
-                    for (int i = 0; i < 4; i++) isz |= br.get_byte() << (8 * i);
                     if (br.overrun()) result = ST_NEED_INPUT;
-                    else if (isz != (uint32_t)pos) result = ST_E_DATA;  // "incorrect length check" (the data check comes first in
-                    expect = t;                                         //  zlib, but both map to the same code)
+                    else {
+                        expect = t;
+                        for (int i = 0; i < 4; i++) isz |= br.get_byte() << (8 * i);
+                        if (br.overrun()) { result = ST_NEED_INPUT; wrap |= 4; }
+                        else if (isz != (uint32_t)pos) result = ST_E_DATA;  // "incorrect length check" (the data check comes
+                    }                                                       //  first in zlib, but both map to the same code)
                 }
             }
             st = SS_FINISH;
@@ -351,7 +356,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_L
         const uint32_t ntok = m.ntok;
         const bool by_kind = P.segment_mode || (P.checks && m.wrap == 0);  // raw units asked for checks: pieces of a longer stream
         const bool want_adler = by_kind ? (P.check_kind & 1) : m.wrap == 1;
-        const bool want_crc = by_kind ? (P.check_kind & 2) : m.wrap == 2;
+        const bool want_crc = by_kind ? (P.check_kind & 2) : (m.wrap & 3) == 2;
         uint64_t opos = 0, ck_pos = 0;
         uint32_t adler = 1, crc = 0;
         uint32_t ti = 0;
@@ -555,6 +560,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_L
                 if (m.wrap == 1 && m.expect != adler) status = ST_E_DATA;  // "incorrect data check"
                 if (m.wrap == 2 && m.expect != crc) status = ST_E_DATA;
             }
+            if (m.wrap == 6 && status == ST_NEED_INPUT && m.expect != crc) status = ST_E_DATA;  // gzip cut inside ISIZE, CRC wrong
             P.out_lens[unit] = opos;
             P.statuses[unit] = status;
             if (P.checks) { P.checks[2 * unit] = adler; P.checks[2 * unit + 1] = crc; }
@@ -593,7 +599,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) inflate_lzw_kernel(TwoPhaseP
         const uint32_t ntok = m.ntok;
         const bool by_kind = P.segment_mode || (P.checks && m.wrap == 0);
         const bool want_adler = by_kind ? (P.check_kind & 1) : m.wrap == 1;
-        const bool want_crc = by_kind ? (P.check_kind & 2) : m.wrap == 2;
+        const bool want_crc = by_kind ? (P.check_kind & 2) : (m.wrap & 3) == 2;
         uint64_t opos = 0, ck_pos = 0;
         uint32_t adler = 1, crc = 0;
         uint32_t ti = 0;
@@ -750,6 +756,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) inflate_lzw_kernel(TwoPhaseP
                 if (m.wrap == 1 && m.expect != adler) status = ST_E_DATA;  // "incorrect data check"
                 if (m.wrap == 2 && m.expect != crc) status = ST_E_DATA;
             }
+            if (m.wrap == 6 && status == ST_NEED_INPUT && m.expect != crc) status = ST_E_DATA;  // gzip cut inside ISIZE, CRC wrong
             P.out_lens[unit] = opos;
             P.statuses[unit] = status;
             if (P.checks) { P.checks[2 * unit] = adler; P.checks[2 * unit + 1] = crc; }
@@ -1016,7 +1023,7 @@ __global__ void __launch_bounds__(W * 32, 3) inflate_lz_cta_kernel(TwoPhaseParam
         // ---- checksums: W slices, folded by thread 0
         const bool by_kind = P.segment_mode || (P.checks && m.wrap == 0);
         const bool want_adler = by_kind ? (P.check_kind & 1) : m.wrap == 1;
-        const bool want_crc = by_kind ? (P.check_kind & 2) : m.wrap == 2;
+        const bool want_crc = by_kind ? (P.check_kind & 2) : (m.wrap & 3) == 2;
         if (want_adler || want_crc) {
             const uint32_t q = ((total + W - 1) / W + 127) & ~127u;
             const uint32_t b0 = warp * q < total ? warp * q : total;
@@ -1055,6 +1062,7 @@ __global__ void __launch_bounds__(W * 32, 3) inflate_lz_cta_kernel(TwoPhaseParam
                 if (m.wrap == 1 && m.expect != adler) status = ST_E_DATA;  // "incorrect data check"
                 if (m.wrap == 2 && m.expect != crc) status = ST_E_DATA;
             }
+            if (m.wrap == 6 && status == ST_NEED_INPUT && m.expect != crc) status = ST_E_DATA;  // gzip cut inside ISIZE, CRC wrong
             P.out_lens[unit] = total;
             P.statuses[unit] = status;
             if (P.checks) { P.checks[2 * unit] = adler; P.checks[2 * unit + 1] = crc; }

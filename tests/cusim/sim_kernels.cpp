@@ -21,6 +21,7 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
     if (!crc_init) { init_crc_tables(&crc); crc_init = true; }
     unsigned long long counter = 0;
     InflateParams P;
+    memset(&P, 0, sizeof P);
     P.in = in; P.in_off = in_off; P.out = out; P.out_off = out_off; P.out_lens = out_lens; P.statuses = statuses;
     P.in_consumed = in_consumed; P.checks = checks; P.counter = &counter; P.crc = &crc; P.n = (uint32_t)n; P.ids = nullptr; P.count_only = 0; P.serial_only = (seed % 4) == 3;
     P.window_bits = window_bits; P.segment_mode = segment_mode; P.check_kind = check_kind;
@@ -63,6 +64,26 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
     }
     return 0;
 }
+
+// One launch of the warp-per-stream kernel in resumable mode (what cz_decode does per call): `in` = staged bytes of the stream
+// from the byte that holds state->bit_pos' origin, `slot` = output slot with the history bytes right in front of it.
+extern "C" int sim_inflate_resume(const uint8_t *in, uint64_t in_len, uint8_t *slot, uint64_t cap, void *state, int window_bits,
+                                  uint64_t *out_len, int32_t *status, uint64_t seed) {
+    static CrcTables crc;
+    static bool crc_init = false;
+    if (!crc_init) { init_crc_tables(&crc); crc_init = true; }
+    unsigned long long counter = 0;
+    const uint64_t in_off[2] = {0, in_len}, out_off[2] = {0, cap};
+    InflateParams P;
+    memset(&P, 0, sizeof P);
+    P.in = in; P.in_off = in_off; P.out = slot; P.out_off = out_off; P.out_lens = out_len; P.statuses = status;
+    P.counter = &counter; P.crc = &crc; P.n = 1; P.serial_only = 1; P.window_bits = window_bits;
+    P.resume = (ResumeState *)state;
+    cusim::set_seed(seed);
+    run_inflate<1, 2>(P, 1);
+    return 0;
+}
+extern "C" uint64_t sim_resume_state_bytes() { return sizeof(ResumeState); }
 
 extern "C" uint32_t sim_crc32_combine(uint32_t a, uint32_t b, uint64_t len2) { return crc32_combine_u(a, b, len2); }
 extern "C" uint32_t sim_adler32_combine(uint32_t a, uint32_t b, uint64_t len2) { return adler32_combine_u(a, b, len2); }
