@@ -10,6 +10,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <thread>
 
 #include "host_common.h"
 #include "inflate_kernel.cuh"
@@ -261,7 +262,20 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
         if (tracing) { cudaEventCreate(&tr.h2d); cudaEventCreate(&tr.k); cudaEventCreate(&tr.d2h); }
         const uint64_t ia = offs[a], ibk = offs[b], oa = offs[n + 1 + a], obk = offs[n + 1 + b];
         if (any_big && !n_small[k] && !n_big[k]) continue;  // every unit of this sub-batch was decoded by the speculative split
-        if (ibk > ia && !CZ_CUDA(cudaMemcpyAsync(w.in.as<uint8_t>() + ia, in + ib + ia, ibk - ia, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
+        if (!skip) {
+            if (ibk > ia && !CZ_CUDA(cudaMemcpyAsync(w.in.as<uint8_t>() + ia, in + ib + ia, ibk - ia, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
+        } else {
+            // units already decoded by the block-parallel path need no copy: the runs between them do
+            size_t i = a;
+            while (i < b) {
+                while (i < b && skip[u0 + i]) i++;
+                size_t e = i;
+                while (e < b && !skip[u0 + e]) e++;
+                const uint64_t ra = offs[i], rb = offs[e];
+                if (rb > ra && !CZ_CUDA(cudaMemcpyAsync(w.in.as<uint8_t>() + ra, in + ib + ra, rb - ra, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
+                i = e;
+            }
+        }
         if (tracing) { cudaEventRecord(tr.h2d, st); tr.in_bytes = ibk - ia; tr.out_bytes = obk - oa; }
         const uint32_t *d_ids = any_big ? (const uint32_t *)(dm + m_ids) + ids_at[k] : nullptr;
         uint8_t *wsk = w.ws.as<uint8_t>() + ws_off[k];
@@ -314,200 +328,7 @@ static void split_by_bytes(size_t n, const uint64_t *off, int parts, std::vector
     cuts[parts] = n;
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Speculative split of ONE long stream. A DEFLATE stream is serial for a decoder lane (a warp manages ~26 MB/s), but streams
-// written with full-flush points — ours (header | segment* | 03 00 | trailer), pigz's, anything using Z_FULL_FLUSH — can be
-// cut after every `00 00 ff ff` marker and the pieces decoded independently. Nothing in the stream says which markers are
-// real, so every step is verified instead of assumed:
-//   1. candidate cuts = occurrences of 00 00 ff ff (thinned to pieces of >= 256 KiB);
-//   2. COUNT pass (the warp-per-stream kernel in counting mode, no output): piece j decoded as a history-free raw fragment must end
-//      exactly at the next cut at a block boundary (=> the cut IS a block boundary) and must never reference bytes before
-//      its own start (=> no history crosses the cut). A failing piece is merged with its neighbours and recounted;
-//   3. with every piece verified and sized, the pieces are decoded in parallel into their final places with per-piece
-//      Adler-32 / CRC-32, the values are folded with the combine identities and compared with the container trailer.
-// If the stream does not split (sync-flush only, no markers, too many failures) the caller decodes it serially.
-struct CountWork {
-    DevBuf in, meta;
-    cudaStream_t stream = nullptr;
-    int dev = -1;
-    bool init(int d) {
-        if (dev == d && stream) return true;
-        dev = d;
-        return CZ_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    }
-    ~CountWork() { if (stream) cudaStreamDestroy(stream); }
-};
-static DevicePool<CountWork, 1> g_count_pool;
-
-// sizes / statuses / consumed bytes of the pieces [in_off[j], in_off[j+1]) of `in`; dev_in_valid: the device copy is current
-static int inflate_count_host(CountWork &w, int dev, const uint8_t *in, uint64_t in_bytes, bool &dev_in_valid, size_t n,
-                              const uint64_t *in_off, int window_bits, int segment_mode, uint64_t *out_lens, int32_t *statuses,
-                              uint64_t *consumed) {
-    DeviceCtx *ctx = device_ctx(dev);
-    if (!ctx) return CZ_E_NO_DEVICE;
-    if (!CZ_CUDA(cudaSetDevice(dev)) || !w.init(dev)) return CZ_E_MEM;
-    // meta: in_off[n+1] caps[n+1] lens[n] consumed[n] statuses[n] | counter 256
-    const size_t m_cap = 8 * (n + 1), m_len = m_cap + 8 * (n + 1), m_cons = m_len + 8 * n, m_stat = m_cons + 8 * n,
-                 m_ws = align_up(m_stat + 4 * n, 256), m_total = m_ws + 256;
-    if (!w.in.reserve(in_bytes + 16) || !w.meta.reserve(m_total)) return CZ_E_MEM;
-    std::vector<uint64_t> h(2 * (n + 1));
-    for (size_t i = 0; i <= n; i++) { h[i] = in_off[i]; h[n + 1 + i] = (uint64_t)i << 40; }  // "unlimited" output slots
-    uint8_t *dm = w.meta.as<uint8_t>();
-    cudaStream_t st = w.stream;
-    if (!dev_in_valid && in_bytes && !CZ_CUDA(cudaMemcpyAsync(w.in.p, in, in_bytes, cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
-    dev_in_valid = true;
-    if (!CZ_CUDA(cudaMemcpyAsync(dm, h.data(), 16 * (n + 1), cudaMemcpyHostToDevice, st))) return CZ_E_MEM;
-    int rc = launch_inflate_count(st, ctx, n, w.in.as<uint8_t>(), (const uint64_t *)dm, (const uint64_t *)(dm + m_cap),
-                                  (uint64_t *)(dm + m_len), (int32_t *)(dm + m_stat), (uint64_t *)(dm + m_cons), window_bits,
-                                  segment_mode, dm + m_ws, 256);
-    if (rc) return rc;
-    if (!CZ_CUDA(cudaMemcpyAsync(out_lens, dm + m_len, 8 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
-    if (!CZ_CUDA(cudaMemcpyAsync(consumed, dm + m_cons, 8 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
-    if (!CZ_CUDA(cudaMemcpyAsync(statuses, dm + m_stat, 4 * n, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
-    if (!CZ_CUDA(cudaStreamSynchronize(st))) return CZ_E_MEM;
-    return 0;
-}
-
-// bytes of container header at the start of `p` (0 = raw), or -1 if it is not a complete, plain header
-static long host_header_len(const uint8_t *p, uint64_t n, int window_bits, int &wrap) {
-    wrap = window_bits < 0 ? 0 : window_bits == 15 ? 1 : window_bits == 31 ? 2 : (n >= 2 && p[0] == 0x1f && p[1] == 0x8b) ? 2 : 1;
-    if (wrap == 0) return 0;
-    if (wrap == 1) {
-        if (n < 2 || (p[0] & 0x0f) != 8 || (p[0] >> 4) > 7 || ((p[0] << 8 | p[1]) % 31) || (p[1] & 0x20)) return -1;
-        return 2;
-    }
-    if (n < 10 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || (p[3] & 0xe0)) return -1;
-    uint64_t o = 10;
-    const int flg = p[3];
-    if (flg & 4) { if (o + 2 > n) return -1; o += 2 + (p[o] | p[o + 1] << 8); }
-    if (flg & 8) { while (o < n && p[o]) o++; o++; }
-    if (flg & 16) { while (o < n && p[o]) o++; o++; }
-    if (flg & 2) o += 2;  // FHCRC: verified only by the serial path; a wrong value still fails there... so refuse
-    if (flg & 2) return -1;
-    return o <= n ? (long)o : -1;
-}
-
-static std::atomic<uint64_t> g_split_ok{0}, g_split_tried{0};  // statistics (cz_split_stats)
-
-static uint64_t huge_unit_bytes() {
-    static uint64_t v = 0;
-    if (!v) {
-        v = 2ull << 20;
-        if (const char *e = getenv("CZ_SPLIT_MIN_KB")) { long k = atol(e); if (k >= 1) v = (uint64_t)k << 10; }
-    }
-    return v;
-}
-
-// true: the unit was decoded (results written). false: not splittable / does not fit — decode it the ordinary way.
-static bool inflate_split_speculative(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t cap, int window_bits,
-                                      uint32_t devices_mask, uint64_t *out_len, int32_t *status, uint64_t *consumed) {
-    int wrap = 0;
-    const long hl = host_header_len(in, in_len, window_bits, wrap);
-    if (hl < 0) return false;
-    // 1. candidate cuts
-    static const uint8_t mark[4] = {0x00, 0x00, 0xff, 0xff};
-    std::vector<uint64_t> cut;
-    cut.push_back((uint64_t)hl);
-    {
-        const uint64_t min_piece = 256u << 10;
-        uint64_t from = (uint64_t)hl;
-        while (from + 4 <= in_len) {
-            const uint8_t *m = (const uint8_t *)memmem(in + from, in_len - from, mark, 4);
-            if (!m) break;
-            const uint64_t c = (uint64_t)(m - in) + 4;
-            if (c - cut.back() >= min_piece) cut.push_back(c);
-            from = (uint64_t)(m - in) + 1;
-        }
-    }
-    if (cut.size() < 3) return false;  // fewer than two verified-able pieces: nothing to gain
-    const int dev = devices_mask ? __builtin_ctz(devices_mask) : 0;
-    CountWork *cwp = g_count_pool.acquire(dev);
-    if (!cwp) return false;
-    struct Lease { CountWork *w; int dev; ~Lease() { g_count_pool.release(dev, w); } } lease{cwp, dev};
-    CountWork &cw = *cwp;
-    bool dev_in_valid = false;
-    int prev = 0;
-    cudaGetDevice(&prev);
-    // 2. count + verify, merging pieces around cuts that do not verify
-    std::vector<uint64_t> lens, cons;
-    std::vector<int32_t> st;
-    uint64_t tail_len = 0, tail_cons = 0;
-    int32_t tail_st = 0;
-    bool ok = false;
-    for (int iter = 0; iter < 4; iter++) {
-        const size_t np = cut.size() - 1;  // pieces [cut[j], cut[j+1]); the tail [cut[np], in_len) holds the final block
-        lens.assign(np, 0); cons.assign(np, 0); st.assign(np, 0);
-        if (inflate_count_host(cw, dev, in, in_len, dev_in_valid, np, cut.data(), -15, 1, lens.data(), st.data(), cons.data())) break;
-        const uint64_t toff[2] = {cut[np], in_len};
-        if (inflate_count_host(cw, dev, in, in_len, dev_in_valid, 1, toff, -15, 0, &tail_len, &tail_st, &tail_cons)) break;
-        if (tail_st != CZ_DECODE_FINISHED) break;  // the end of the stream is not where the last cut says: not ours to split
-        // a false cut makes BOTH pieces around it fail (the one before runs out of input mid-block, the one after starts on
-        // garbage), so a failing piece loses its start and its end cut; true cuts lost that way only make pieces coarser
-        std::vector<uint8_t> bad_piece(np, 0);
-        size_t bad = 0;
-        for (size_t j = 0; j < np; j++)
-            if (!(st[j] == CZ_DECODE_FINISHED && cons[j] == cut[j + 1] - cut[j])) { bad_piece[j] = 1; bad++; }
-        if (bad == 0) { ok = true; break; }
-        if (bad * 4 > np) break;  // mostly failures: sync-flush points (history crosses them), not full-flush ones
-        std::vector<uint64_t> keep;
-        keep.push_back(cut[0]);
-        for (size_t k = 1; k < np; k++)
-            if (!bad_piece[k - 1] && !bad_piece[k]) keep.push_back(cut[k]);
-        keep.push_back(cut[np]);
-        if (keep.size() < 3) break;
-        cut.swap(keep);
-    }
-    cudaSetDevice(prev);
-    if (!ok) return false;
-    const size_t np = cut.size() - 1;
-    uint64_t total = tail_len;
-    for (size_t j = 0; j < np; j++) total += lens[j];
-    if (total > cap) return false;  // the ordinary path reports NeedOutput with the exact partial output
-    // 3. decode the verified pieces in parallel, straight into place
-    std::vector<uint64_t> in_off(cut), out_off(np + 2, 0), got(np + 1, 0);
-    in_off.push_back(in_len);  // piece np = the tail
-    for (size_t j = 0; j < np; j++) out_off[j + 1] = out_off[j] + lens[j];
-    out_off[np + 1] = out_off[np] + tail_len;
-    std::vector<int32_t> pst(np + 1, 0);
-    std::vector<uint32_t> chk(2 * (np + 1), 0);
-    std::vector<uint64_t> pcons(np + 1, 0);
-    if (inflate_batch_host(np, in, in_off.data(), out, out_off.data(), got.data(), pst.data(), nullptr, -15, 1, chk.data(), devices_mask))
-        return false;
-    if (inflate_batch_host(1, in, in_off.data() + np, out, out_off.data() + np, got.data() + np, pst.data() + np, pcons.data() + np, -15,
-                           0, chk.data() + 2 * np, devices_mask))
-        return false;
-    uint32_t adler = 1, crc = 0;
-    for (size_t j = 0; j <= np; j++) {
-        if (pst[j] != CZ_DECODE_FINISHED || got[j] != out_off[j + 1] - out_off[j]) return false;  // (cannot happen after the count pass)
-        adler = czk::adler32_combine_u(adler, chk[2 * j], got[j]);
-        crc = czk::crc32_combine_u(crc, chk[2 * j + 1], got[j]);
-    }
-    // container trailer right after the final block
-    uint64_t end = cut[np] + pcons[np];
-    int32_t fin = CZ_DECODE_FINISHED;
-    if (wrap == 1) {
-        if (end + 4 > in_len) fin = CZ_DECODE_NEED_INPUT;
-        else {
-            const uint8_t *t = in + end;
-            if (((uint32_t)t[0] << 24 | (uint32_t)t[1] << 16 | (uint32_t)t[2] << 8 | t[3]) != adler) fin = CZ_E_DATA;
-            end += 4;
-        }
-    } else if (wrap == 2) {
-        if (end + 8 > in_len) fin = CZ_DECODE_NEED_INPUT;
-        else {
-            const uint8_t *t = in + end;
-            const uint32_t c = (uint32_t)t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
-            const uint32_t isz = (uint32_t)t[4] | (uint32_t)t[5] << 8 | (uint32_t)t[6] << 16 | (uint32_t)t[7] << 24;
-            if (c != crc || isz != (uint32_t)total) fin = CZ_E_DATA;
-            end += 8;
-        }
-    }
-    if (fin == CZ_DECODE_NEED_INPUT) end = in_len;
-    *out_len = total;
-    *status = fin;
-    if (consumed) *consumed = end;
-    return true;
-}
+static std::atomic<uint64_t> g_split_ok{0}, g_split_tried{0};  // long units: tried / decoded by the block-parallel path
 
 int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint8_t *out, const uint64_t *out_off,
                        uint64_t *out_lens, int32_t *statuses, uint64_t *in_consumed, int window_bits, int segment_mode,
@@ -519,23 +340,40 @@ int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint
         if (devices_mask >> d & 1) devs.push_back(d);
     for (int d : devs)
         if (!device_ctx(d)) return CZ_E_NO_DEVICE;
-    // long single streams first: split speculatively at full-flush markers where that verifies (see above)
+    std::vector<size_t> cuts;
+    split_by_bytes(n, in_off, (int)devs.size(), cuts);
+    // Long streams first: the block-parallel path (inflate_runs.cuh) decodes them run by run on their shard's device. What it
+    // declines (errors, truncation, slots that are too small) stays in the batch for the serial kernels below.
     std::vector<uint8_t> skip;
     struct Done { size_t i; uint64_t len, cons; int32_t st; };
     std::vector<Done> done;
-    static const bool no_split = getenv("CZ_NO_SPLIT") != nullptr;
-    if (!segment_mode && !checks && !no_split) {
-        for (size_t i = 0; i < n; i++) {
-            if (in_off[i + 1] - in_off[i] < huge_unit_bytes()) continue;
-            Done d{i, 0, 0, 0};
-            g_split_tried++;
-            if (inflate_split_speculative(in + in_off[i], in_off[i + 1] - in_off[i], out + out_off[i], out_off[i + 1] - out_off[i],
-                                          window_bits, devices_mask, &d.len, &d.st, &d.cons)) {
-                g_split_ok++;
-                if (skip.empty()) skip.assign(n, 0);
-                skip[i] = 1;
-                done.push_back(d);
+    static const bool no_runs = getenv("CZ_NO_RUNS") != nullptr || getenv("CZ_NO_SPLIT") != nullptr;
+    if (!segment_mode && !checks && !no_runs) {
+        std::vector<std::vector<size_t>> long_ids(devs.size());
+        bool any = false;
+        for (size_t k = 0; k < devs.size(); k++)
+            for (size_t i = cuts[k]; i < cuts[k + 1]; i++)
+                if (in_off[i + 1] - in_off[i] >= runs_min_unit_bytes()) { long_ids[k].push_back(i); any = true; }
+        if (any) {
+            skip.assign(n, 0);
+            std::vector<uint64_t> cons(n, 0);
+            std::vector<int> rcs(devs.size(), 0);
+            auto work = [&](size_t k) {
+                rcs[k] = inflate_long_units(devs[k], long_ids[k], in, in_off, out, out_off, out_lens, statuses, cons.data(), window_bits, skip.data());
+            };
+            std::vector<std::thread> th;
+            for (size_t k = 1; k < devs.size(); k++)
+                if (!long_ids[k].empty()) th.emplace_back(work, k);
+            if (!long_ids[0].empty()) work(0);
+            for (auto &t : th) t.join();
+            for (size_t k = 0; k < devs.size(); k++) {
+                if (rcs[k]) return rcs[k];
+                for (size_t i : long_ids[k]) {
+                    g_split_tried++;
+                    if (skip[i]) { g_split_ok++; done.push_back(Done{i, out_lens[i], cons[i], statuses[i]}); }
+                }
             }
+            if (done.empty()) skip.clear();
         }
     }
     // one work object (streams, device and pinned buffers) per device, borrowed from a bounded per-device pool
@@ -549,8 +387,6 @@ int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint
         if (!(works[d] = pool.acquire(d))) { set_error("out of memory"); return CZ_E_MEM; }
     int prev = 0;
     cudaGetDevice(&prev);
-    std::vector<size_t> cuts;
-    split_by_bytes(n, in_off, (int)devs.size(), cuts);
     int rc = 0;
     // enqueue every shard first (copies and kernels of different devices overlap), then wait for all
     for (size_t k = 0; k < devs.size() && !rc; k++)
@@ -808,19 +644,24 @@ extern "C" cz_result cz_decode(void *state, const uint8_t *in, size_t in_len, ui
     if (s->error) { r.status = s->error; return r; }         // zlib: mode BAD stays BAD
     if (s->done) { r.status = CZ_DECODE_FINISHED; return r; }  // zlib: mode DONE returns Z_STREAM_END again, nothing consumed
     // a large stream that arrives whole at the very start: the batched path (speculative split at verified full-flush points)
-    static const bool no_split = getenv("CZ_NO_SPLIT") != nullptr;
+    static const bool no_runs = getenv("CZ_NO_RUNS") != nullptr || getenv("CZ_NO_SPLIT") != nullptr;
     const bool fresh = s->rs.phase == czk::RP_HEADER && s->rs.total_out == 0 && s->carry.empty();
-    if (fresh && !no_split && in_len >= huge_unit_bytes()) {
+    if (fresh && !no_runs && in_len >= (1u << 20)) {
+        const uint64_t ioff[2] = {0, in_len}, ooff[2] = {0, out_len};
         uint64_t got = 0, used = 0;
         int32_t st = 0;
+        uint8_t done1 = 0;
+        int prev = 0;
+        cudaGetDevice(&prev);
         g_split_tried++;
-        if (inflate_split_speculative(in, in_len, out, out_len, s->window_bits, 1u << s->dev, &got, &st, &used) &&
-            (st == CZ_DECODE_FINISHED || st == CZ_E_DATA)) {
+        const int rc = inflate_long_units(s->dev, std::vector<size_t>(1, 0), in, ioff, out, ooff, &got, &st, &used, s->window_bits, &done1);
+        cudaSetDevice(prev);
+        if (rc == 0 && done1) {  // the whole stream, bit-exact and checked: Finished; what follows it goes back to the caller
             g_split_ok++;
+            s->done = true;
             r.output_remain = out_len - (size_t)got;
-            if (st == CZ_DECODE_FINISHED) { s->done = true; r.input_remain = in_len - (size_t)used; }
-            else s->error = st;
-            r.status = st;
+            r.input_remain = in_len - (size_t)used;
+            r.status = CZ_DECODE_FINISHED;
             return r;
         }
     }

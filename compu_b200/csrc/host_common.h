@@ -101,6 +101,12 @@ int launch_inflate_resume(cudaStream_t st, DeviceCtx *ctx, const uint8_t *d_in, 
                           const uint64_t *d_out_off, uint64_t *d_out_lens, int32_t *d_statuses, int window_bits,
                           czk::ResumeState *d_resume, void *d_ws);
 
+// block-parallel path for long streams (inflate.cu, inflate_runs_host.h)
+uint64_t runs_min_unit_bytes();
+int inflate_long_units(int dev, const std::vector<size_t> &ids, const uint8_t *in, const uint64_t *in_off, uint8_t *out,
+                       const uint64_t *out_off, uint64_t *out_lens, int32_t *statuses, uint64_t *in_consumed, int window_bits,
+                       uint8_t *done);
+
 // batched inflate over host memory (host.cu); segment_mode / checks as in cz_inflate_segments_device
 int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint8_t *out, const uint64_t *out_off,
                        uint64_t *out_lens, int32_t *statuses, uint64_t *in_consumed, int window_bits, int segment_mode,

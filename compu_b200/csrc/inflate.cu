@@ -7,6 +7,7 @@
 #include "inflate_lane_kernel.cuh"
 #include "inflate_lc_kernel.cuh"
 #include "inflate_two_phase.cuh"
+#include "inflate_runs_host.h"
 
 namespace czh {
 
@@ -213,6 +214,156 @@ int launch_inflate_count(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_
     P.count_only = 1; P.serial_only = par_decode_off();
     if (!CZ_CUDA(cudaMemsetAsync(d_ws, 0, 256, st))) return CZ_E_MEM;
     return launch_cfg<1, 8>(st, ctx, P);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Block-parallel inflate of long streams: the CUDA backend of inflate_runs_host.h and the per-device driver.
+struct CudaRunsBackend {
+    DeviceCtx *ctx = nullptr;
+    cudaStream_t st = nullptr;
+    DevBuf in, out, arena;
+    size_t used = 0;
+    int per_sm_tok = 0, per_sm_lz16 = 0;
+    bool configured = false;
+    ~CudaRunsBackend() { if (st) cudaStreamDestroy(st); }
+    bool init(DeviceCtx *c) {
+        ctx = c;
+        if (!st && !CZ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking))) return false;
+        if (!configured) {
+            auto ka = czk::inflate_tok_kernel<14>;
+            auto kl = czk::inflate_tok_kernel<4>;
+            if (!CZ_CUDA(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)czk::inflate_tok_smem_bytes<14>())) ||
+                !CZ_CUDA(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)czk::inflate_tok_smem_bytes<4>())) ||
+                !CZ_CUDA(cudaFuncSetAttribute(czk::inflate_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CZK_WINDOW_SMEM)) ||
+                !CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tok, ka, 14 * 32, czk::inflate_tok_smem_bytes<14>())) ||
+                !CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lz16, czk::inflate_lz16_kernel<8>, 256, 0))) return false;
+            if (per_sm_tok < 1 || per_sm_lz16 < 1) { set_error("run-mode inflate kernels do not fit on an SM"); return false; }
+            configured = true;
+        }
+        return true;
+    }
+    uint8_t *d_in() { return in.as<uint8_t>(); }
+    uint8_t *d_out() { return out.as<uint8_t>(); }
+    void scratch_reset() { used = 0; }
+    bool scratch_need(size_t total) { return arena.reserve(total + 4096); }
+    bool out_need(size_t bytes) { return out.reserve(bytes); }
+    void *scratch(size_t bytes) {
+        const size_t a = (used + 255) & ~(size_t)255;
+        if (a + bytes > arena.cap) { set_error("internal: run scratch arena too small"); return nullptr; }
+        used = a + bytes;
+        return arena.as<uint8_t>() + a;
+    }
+    bool h2d(void *d, const void *h, size_t n) { return !n || (CZ_CUDA(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, st)) && CZ_CUDA(cudaStreamSynchronize(st))); }
+    bool d2h(void *h, const void *d, size_t n) { return !n || (CZ_CUDA(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, st)) && CZ_CUDA(cudaStreamSynchronize(st))); }
+    bool zero(void *d, size_t n) { return CZ_CUDA(cudaMemsetAsync(d, 0, n, st)); }
+    const czk::CrcTables *crc() { return ctx->d_crc; }
+    bool ok() { return CZ_CUDA(cudaGetLastError()); }
+    bool candidates(const czk::CandChunk *c, uint32_t n, uint64_t *cand) {
+        CZ_KL(czk::inflate_candidates_kernel<<<(n + 3) / 4, 128, 0, st>>>(d_in(), c, n, cand));
+        return ok();
+    }
+    bool tok(const czk::TwoPhaseParams &Q) {
+        const uint32_t n = Q.base.n;
+        // few runs: 4 warps per CTA spread over the SMs (a lane decodes sooner when its warp shares the schedulers with 3 others)
+        if (n <= (uint32_t)ctx->sm_count * 32 * 4 * 2) CZ_KL(czk::inflate_tok_kernel<4><<<(n + 127) / 128, 128, czk::inflate_tok_smem_bytes<4>(), st>>>(Q));
+        else {
+            uint64_t g = (n + 32 * 14 - 1) / (32 * 14), gmax = (uint64_t)ctx->sm_count * per_sm_tok;
+            if (g > gmax) g = gmax;
+            CZ_KL(czk::inflate_tok_kernel<14><<<(unsigned)g, 14 * 32, czk::inflate_tok_smem_bytes<14>(), st>>>(Q));
+        }
+        return ok();
+    }
+    bool lz16(const czk::TwoPhaseParams &Q, uint16_t *sym) {
+        uint64_t g = (Q.base.n + 7) / 8, gmax = (uint64_t)ctx->sm_count * per_sm_lz16;
+        if (g > gmax) g = gmax;
+        CZ_KL(czk::inflate_lz16_kernel<8><<<(unsigned)g, 256, 0, st>>>(Q, sym));
+        return ok();
+    }
+    bool window(const czk::RunStream *s, uint32_t ns, const uint64_t *run_off, const uint16_t *sym, uint8_t *win, uint32_t *bad) {
+        if (!ns) return true;
+        CZ_KL(czk::inflate_window_kernel<<<ns, 1024, CZK_WINDOW_SMEM, st>>>(s, run_off, sym, win, bad));
+        return ok();
+    }
+    bool resolve(const czk::RunSlice *sl, uint32_t nsl, const uint64_t *run_off, const uint64_t *final_off, const uint8_t *first,
+                 const uint16_t *sym, const uint8_t *win, uint8_t *o, uint32_t *bad) {
+        if (!nsl) return true;
+        CZ_KL(czk::inflate_resolve_kernel<<<nsl, 256, 0, st>>>(sl, nsl, run_off, final_off, first, sym, win, o, bad));
+        return ok();
+    }
+    bool check(const uint64_t *run_off, const uint64_t *final_off, uint32_t n, const uint8_t *o, int kind, uint32_t *checks) {
+        CZ_KL(czk::inflate_run_check_kernel<8><<<(n + 7) / 8, 256, 0, st>>>(run_off, final_off, n, o, ctx->d_crc, kind, checks));
+        return ok();
+    }
+};
+
+static uint64_t runs_chunk_bytes() {
+    static const uint64_t v = [] { const char *e = getenv("CZ_RUN_CHUNK_KB"); long k = e ? atol(e) : 0; return k >= 4 ? (uint64_t)k << 10 : (uint64_t)(64u << 10); }();
+    return v;
+}
+uint64_t runs_min_unit_bytes() { return 2 * runs_chunk_bytes(); }
+
+// Decodes the long streams `ids` of a packed host batch on device `dev` with the block-parallel path, in batches bounded by
+// device memory. done[i] = 1 for the units it decoded (out, out_lens, statuses = Finished, in_consumed written); the others
+// are left untouched for the serial path.
+int inflate_long_units(int dev, const std::vector<size_t> &ids, const uint8_t *in, const uint64_t *in_off, uint8_t *out,
+                       const uint64_t *out_off, uint64_t *out_lens, int32_t *statuses, uint64_t *in_consumed, int window_bits,
+                       uint8_t *done) {
+    DeviceCtx *ctx = device_ctx(dev);
+    if (!ctx) return CZ_E_NO_DEVICE;
+    if (ids.empty()) return 0;
+    static DevicePool<CudaRunsBackend, 1> pool;
+    if (!CZ_CUDA(cudaSetDevice(dev))) return CZ_E_MEM;
+    CudaRunsBackend *bk = pool.acquire(dev);
+    if (!bk) return CZ_E_MEM;
+    struct Lease { CudaRunsBackend *b; int dev; DevicePool<CudaRunsBackend, 1> *p; ~Lease() { p->release(dev, b); } } lease{bk, dev, &pool};
+    if (!bk->init(ctx)) return CZ_E_MEM;
+    const uint64_t batch_out = 2048ull << 20, batch_in = 1024ull << 20;
+    size_t a = 0;
+    while (a < ids.size()) {
+        // a batch: bounded by (the callers' slots as a proxy for) output and by input bytes
+        size_t b = a;
+        uint64_t in_bytes = 0, cap_bytes = 0;
+        while (b < ids.size()) {
+            const uint64_t il = in_off[ids[b] + 1] - in_off[ids[b]], ol = out_off[ids[b] + 1] - out_off[ids[b]];
+            if (b > a && (in_bytes + il > batch_in || cap_bytes + ol > batch_out)) break;
+            in_bytes += runs_align(il + 64); cap_bytes += ol;
+            b++;
+        }
+        std::vector<BigUnit> units(b - a);
+        if (!bk->in.reserve(in_bytes + 256)) return 0;  // no memory for this batch: the serial path takes these units
+        uint64_t o = 0;
+        bool copied = true;
+        for (size_t k = a; k < b; k++) {
+            BigUnit &U = units[k - a];
+            const size_t i = ids[k];
+            U.h_in = in + in_off[i]; U.in_len = in_off[i + 1] - in_off[i]; U.d_in_lo = o;
+            U.out_cap = out_off[i + 1] - out_off[i]; U.window_bits = window_bits;
+            copied = copied && CZ_CUDA(cudaMemcpyAsync(bk->d_in() + o, U.h_in, U.in_len, cudaMemcpyHostToDevice, bk->st));
+            o += runs_align(U.in_len + 64);
+        }
+        if (!copied || !CZ_CUDA(cudaStreamSynchronize(bk->st))) return CZ_E_MEM;
+        const int rc = inflate_runs_batch(*bk, units, runs_chunk_bytes());
+        if (rc == 0) {
+            bool ok = true;
+            for (size_t k = a; k < b; k++) {
+                const BigUnit &U = units[k - a];
+                if (!U.ok) continue;
+                const size_t i = ids[k];
+                if (U.out_len) ok = ok && CZ_CUDA(cudaMemcpyAsync(out + out_off[i], bk->d_out() + U.d_out_off, U.out_len, cudaMemcpyDeviceToHost, bk->st));
+            }
+            if (!ok || !CZ_CUDA(cudaStreamSynchronize(bk->st))) return CZ_E_MEM;
+            for (size_t k = a; k < b; k++) {
+                const BigUnit &U = units[k - a];
+                if (!U.ok) continue;
+                const size_t i = ids[k];
+                out_lens[i] = U.out_len; statuses[i] = CZ_DECODE_FINISHED;
+                if (in_consumed) in_consumed[i] = U.in_consumed;
+                done[i] = 1;
+            }
+        } else cudaGetLastError();  // (out of scratch memory etc.: the serial path takes the batch)
+        a = b;
+    }
+    return 0;
 }
 
 // One resumable unit (the streaming Decoder): the warp-per-stream kernel with its ResumeState. d_ws: 256 bytes.

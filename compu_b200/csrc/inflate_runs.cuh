@@ -1,0 +1,382 @@
+// inflate_runs.cuh — block-parallel inflate of LONG streams (any producer: zlib, zlib-ng, pigz, ours).
+//
+// A DEFLATE stream is serial for a decoder: a lane of phase A manages a few MB/s, a whole warp ~20 MB/s. But the blocks of a
+// stream are independent for the HUFFMAN part once their first bit is known, and phase A's tokens do not depend on history.
+// So a long stream is cut into RUNS of blocks and every run goes through the two-phase path like a small stream of its own:
+//
+//   1. inflate_candidates_kernel   one warp per chunk of compressed bytes: the first bit offset in the chunk at which a
+//                                  complete, valid dynamic-block header parses (BFINAL = 0, BTYPE = 10, HLIT / HDIST in range,
+//                                  a COMPLETE code-length code, code lengths that decode to complete literal/length and
+//                                  distance codes with an end-of-block symbol). Lane = bit offset, 32 offsets per step.
+//   2. phase A in RUN mode         (inflate_tok_kernel, TwoPhaseParams::runs) from every candidate to the first block boundary
+//                                  at or after the next candidate — first only counting (sizes, end positions), then, with
+//                                  the output and token offsets known, emitting tokens. The host checks that run r ends
+//                                  exactly where run r+1 starts; a candidate that is not on the chain is a false positive and
+//                                  its range is decoded again from the true boundary (inflate.cu).
+//   3. inflate_lz16_kernel         phase B per run into 16-bit symbols: a byte, or a MARKER 0x8000 | w for a byte that lies
+//                                  before the run, w = its offset in the 32 KiB window that precedes the run. Copies of
+//                                  markers copy the marker, so after this pass every position names its final source.
+//   4. inflate_window_kernel       per stream, run after run: the last 32 KiB of run r with its markers replaced through
+//                                  the window of run r-1 — 32 K independent look-ups per run, the only serial step.
+//   5. inflate_resolve_kernel      every run in parallel: symbols -> bytes through the window in front of the run, 16-byte
+//                                  stores into the final output; Adler-32 / CRC-32 per run, folded by the host with the
+//                                  combine identities and compared with the container trailer.
+//
+// The approach follows the published two-stage scheme of parallel gzip decompressors (candidate block search + marker
+// replacement); the kernels and the chain verification are written for this library.
+#pragma once
+#include "inflate_two_phase.cuh"
+
+namespace czk {
+
+// ---------------------------------------------------------------------------------------------------------------
+// 1. candidate search
+struct CandChunk {
+    uint64_t lo_bit, hi_bit;   // search [lo_bit, hi_bit), absolute bit indices into `in`
+    uint64_t end_bit;          // end of the stream the chunk belongs to (nothing may be read as data beyond it)
+};
+
+// n bits (n <= 25) at absolute bit position pos of `in` (two aligned word loads; the caller keeps pos + n <= end)
+__device__ __forceinline__ uint32_t cand_bits(const uint32_t *words, uint64_t pos, uint32_t n) {
+    const uint64_t wi = pos >> 5;
+    const uint32_t sh = (uint32_t)(pos & 31);
+    const uint32_t lo = __ldg(words + wi), hi = __ldg(words + wi + 1);
+    return __funnelshift_r(lo, hi, sh) & ((1u << n) - 1u);
+}
+
+// Full check of a dynamic block header at absolute bit `b` (the cheap filters have passed). Lane-serial, rare.
+__device__ inline bool cand_full_check(const uint32_t *words, uint64_t b, uint64_t end_bit, uint32_t hlit, uint32_t hdist, uint32_t hclen) {
+    uint64_t pos = b + 17;
+    if (pos + 3ull * hclen > end_bit) return false;
+    // code-length code: lengths in the permuted order, canonical codes, 128-entry table: symbol << 3 | length
+    const uint64_t order_lo = 16ull | (17ull << 5) | (18ull << 10) | (0ull << 15) | (8ull << 20) | (7ull << 25) |
+                              (9ull << 30) | (6ull << 35) | (10ull << 40) | (5ull << 45) | (11ull << 50) | (4ull << 55);
+    const uint64_t order_hi = 12ull | (3ull << 5) | (13ull << 10) | (2ull << 15) | (14ull << 20) | (1ull << 25) | (15ull << 30);
+    uint64_t cl_lens = 0;
+    for (uint32_t i = 0; i < hclen; i++) {
+        const uint32_t l = cand_bits(words, pos, 3);
+        pos += 3;
+        const uint32_t sym = i < 12 ? (uint32_t)(order_lo >> (5 * i)) & 31 : (uint32_t)(order_hi >> (5 * (i - 12))) & 31;
+        cl_lens |= (uint64_t)l << (3 * sym);
+    }
+    uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t s = 0; s < 19; s++) cnt[(cl_lens >> (3 * s)) & 7]++;
+    uint32_t next[8], code = 0;
+    int left = 1;
+    for (uint32_t len = 1; len <= 7; len++) {
+        left = (left << 1) - (int)cnt[len];
+        if (left < 0) return false;
+        next[len] = code;
+        code = (code + cnt[len]) << 1;
+    }
+    if (left != 0) return false;  // zlib: an incomplete code-length code is always an error
+    uint8_t cl_tab[128];
+    for (uint32_t s = 0; s < 19; s++) {
+        const uint32_t l = (uint32_t)(cl_lens >> (3 * s)) & 7;
+        if (!l) continue;
+        const uint32_t c = next[l]++;
+        const uint32_t rev = __brev(c) >> (32 - l);
+        for (uint32_t idx = rev; idx < 128; idx += (1u << l)) cl_tab[idx] = (uint8_t)((s << 3) | l);
+    }
+    // the code lengths themselves: Kraft sums of both alphabets on the fly, so random bits fail after a few symbols
+    const uint32_t nlit = hlit + 257, total = nlit + hdist + 1;
+    uint32_t i = 0, prev = 0, lit_sum = 0, dist_sum = 0, eob_len = 0, dist_codes = 0;
+    while (i < total) {
+        if (pos + 14 > end_bit) return false;
+        const uint32_t e = cl_tab[cand_bits(words, pos, 7)];
+        pos += e & 7;
+        const uint32_t s = e >> 3;
+        uint32_t rep = 1, val = s;
+        if (s == 16) {
+            if (i == 0) return false;
+            rep = 3 + cand_bits(words, pos, 2); pos += 2; val = prev;
+        } else if (s == 17) { rep = 3 + cand_bits(words, pos, 3); pos += 3; val = 0; }
+        else if (s == 18) { rep = 11 + cand_bits(words, pos, 7); pos += 7; val = 0; }
+        if (i + rep > total) return false;
+        if (val) {
+            const uint32_t w = 1u << (15 - val);
+            // symbols i .. i+rep-1: those below nlit belong to the literal/length alphabet
+            const uint32_t nl = i >= nlit ? 0u : (i + rep <= nlit ? rep : nlit - i);
+            lit_sum += nl * w;
+            dist_sum += (rep - nl) * w;
+            dist_codes += rep - nl;
+            if (lit_sum > 32768u || dist_sum > 32768u) return false;  // over-subscribed
+            if (i <= 256 && i + rep > 256) eob_len = val;
+        }
+        i += rep;
+        prev = val;
+    }
+    if (!eob_len) return false;              // "missing end-of-block"
+    if (lit_sum != 32768u) return false;     // incomplete literal/length code (a one-symbol code is legal but never worth a cut)
+    if (!(dist_sum == 32768u || dist_sum == 0u || (dist_sum == 16384u && dist_codes == 1))) return false;
+    return true;
+}
+
+// cand[c] = absolute bit of the first plausible dynamic block header in chunk c, or ~0.
+__global__ void __launch_bounds__(128) inflate_candidates_kernel(const uint8_t *in, const CandChunk *chunks, uint32_t n_chunks, uint64_t *cand) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n_chunks) return;
+    const CandChunk ch = chunks[c];
+    const uint32_t *words = (const uint32_t *)in;  // `in` is the (256-byte aligned) base of the device input buffer
+    uint64_t found = ~0ull;
+    for (uint64_t base = ch.lo_bit; base < ch.hi_bit && found == ~0ull; base += 32) {
+        const uint64_t b = base + lane;
+        bool ok = b < ch.hi_bit && b + 17 + 12 <= ch.end_bit;
+        uint32_t hlit = 0, hdist = 0, hclen = 0;
+        if (ok) {
+            const uint32_t h = cand_bits(words, b, 17);
+            hlit = (h >> 3) & 31; hdist = (h >> 8) & 31; hclen = ((h >> 13) & 15) + 4;
+            ok = (h & 7u) == 4u && hlit <= 29 && hdist <= 29;  // BFINAL = 0, BTYPE = 10
+        }
+        if (ok) ok = cand_full_check(words, b, ch.end_bit, hlit, hdist, hclen);
+        const uint32_t m = __ballot_sync(CZK_FULL, ok);
+        if (m) found = base + (uint32_t)(__ffs((int)m) - 1);
+    }
+    if (lane == 0) cand[c] = found;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 3. phase B of a run into 16-bit symbols (the token-parallel resolution of inflate_lz_kernel, on symbols)
+#define CZK_MARK 0x8000u
+
+// symbol at run-relative index idx of S (idx < 0: a byte in front of the run -> its marker)
+__device__ __forceinline__ uint32_t run_sym(const uint16_t *S, int64_t idx) {
+    return idx < 0 ? (CZK_MARK | (uint32_t)(32768 + idx)) : (uint32_t)S[idx];
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_LZ_MINB : 1)) inflate_lz16_kernel(TwoPhaseParams Q, uint16_t *sym) {
+    const InflateParams &P = Q.base;
+    const uint32_t lane = threadIdx.x & 31;
+    constexpr int SHORT = CZK_LZ_SHORT;
+    for (;;) {
+        unsigned long long u64 = 0;
+        if (lane == 0) u64 = atomicAdd(Q.counter_b, 1ull);
+        u64 = __shfl_sync(CZK_FULL, u64, 0);
+        if (u64 >= P.n) break;
+        const uint32_t unit = P.ids ? P.ids[u64] : (uint32_t)u64;
+        const uint64_t o0 = P.out_off[unit];
+        const TokMeta m = Q.meta[unit];
+        uint16_t *S = sym + (o0 - P.out_off[0]);             // symbols of this run
+        const uint8_t *ib = P.in + Q.runs[unit].in_lo;        // stored runs reference the stream's input
+        const uint32_t *tok = Q.tok + tok_word_off(o0 - P.out_off[0], unit);
+        const uint32_t ntok = m.ntok;
+        uint64_t opos = 0;
+        uint32_t ti = 0;
+        while (ti < ntok) {
+            const uint32_t t_raw = ti + lane < ntok ? tok[ti + lane] : CZK_TOK_STORED;
+            const uint32_t stopm = __ballot_sync(CZK_FULL, (t_raw >> 30) == 3u);
+            const uint32_t nt = stopm ? (uint32_t)__ffs(stopm) - 1u : 32u;
+            if (nt) {
+                const uint32_t t = lane < nt ? t_raw : 0u;
+                const uint32_t tl = (t >> 31) ? ((t >> 24) & 3u) : (t & 0x1ffu);
+                uint32_t pos = tl;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    uint32_t v = __shfl_up_sync(CZK_FULL, pos, d);
+                    if ((int)lane >= d) pos += v;
+                }
+                const uint32_t total = __shfl_sync(CZK_FULL, pos, 31);
+                pos -= tl;
+                const int64_t base = (int64_t)opos;  // run-relative index of this group's first symbol
+                const bool is_tok = lane < nt;
+                const bool is_lit = is_tok && (t >> 31);
+                const uint32_t dist = (t >> 9) & 0xffffu;
+                const int ipos = (int)pos;
+                const int src0 = ipos - (int)dist;
+                int dep_end = 0;
+                if (is_tok && !is_lit) { dep_end = src0 + (int)tl; if (dep_end > ipos) dep_end = ipos; }
+                const bool coop = is_tok && !is_lit && (tl > (uint32_t)SHORT || dist < tl);
+                bool done = !is_tok;
+                for (;;) {
+                    const uint32_t undone = __ballot_sync(CZK_FULL, !done);
+                    if (!undone) break;
+                    const int first = __ffs((int)undone) - 1;
+                    const int frontier = __shfl_sync(CZK_FULL, ipos, first);
+                    const bool ready = !done && dep_end <= frontier;
+                    if (ready && !coop) {
+                        uint16_t *d = S + base + ipos;
+                        if (is_lit) {
+                            d[0] = (uint16_t)(t & 0xff);
+                            if (tl > 1) d[1] = (uint16_t)((t >> 8) & 0xff);
+                            if (tl > 2) d[2] = (uint16_t)((t >> 16) & 0xff);
+                        } else {
+                            uint32_t bb[SHORT];
+#pragma unroll
+                            for (int k = 0; k < SHORT; k++) bb[k] = k < (int)tl ? run_sym(S, base + src0 + k) : 0u;
+#pragma unroll
+                            for (int k = 0; k < SHORT; k++) if (k < (int)tl) d[k] = (uint16_t)bb[k];
+                        }
+                    }
+                    uint32_t cm = __ballot_sync(CZK_FULL, ready && coop);
+                    while (cm) {
+                        const int sl = __ffs((int)cm) - 1;
+                        cm &= cm - 1;
+                        const uint32_t Ln = __shfl_sync(CZK_FULL, tl, sl), D = __shfl_sync(CZK_FULL, dist, sl);
+                        const int P0 = __shfl_sync(CZK_FULL, ipos, sl);
+                        uint16_t *d = S + base + P0;
+                        const int64_t s0 = base + P0 - (int64_t)D;  // symbols [s0, s0 + D) are complete
+                        if (D >= Ln) {
+                            for (uint32_t k = lane; k < Ln; k += 32) d[k] = (uint16_t)run_sym(S, s0 + k);
+                        } else if (D >= 32) {
+                            for (uint32_t k0 = 0; k0 < Ln; k0 += 32) {
+                                const uint32_t k = k0 + lane;
+                                if (k < Ln) d[k] = (uint16_t)run_sym(S, s0 + k);
+                                __syncwarp();
+                            }
+                        } else {
+                            uint32_t r = lane % D;
+                            const uint32_t stepD = 32u % D;
+                            for (uint32_t k = lane; k < Ln; k += 32) {
+                                d[k] = (uint16_t)run_sym(S, s0 + r);
+                                r += stepD;
+                                if (r >= D) r -= D;
+                            }
+                        }
+                    }
+                    done = done || ready;
+                    __syncwarp();
+                }
+                opos += total;
+                ti += nt;
+            }
+            if (nt < 32 && ti < ntok) {
+                const uint32_t w0 = tok[ti], w1 = tok[ti + 1], w2 = tok[ti + 2];
+                const uint32_t n = w0 & 0xffffu;
+                const uint64_t ipos_in = (uint64_t)(w1 & 0x1fffffffu) | ((uint64_t)(w2 & 0x1fffffffu) << 29);
+                for (uint32_t k = lane; k < n; k += 32) S[opos + k] = (uint16_t)ib[ipos_in + k];
+                __syncwarp();
+                opos += n;
+                ti += 3;
+            }
+        }
+        if (lane == 0) {
+            P.out_lens[unit] = opos;
+            P.statuses[unit] = m.status;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 4. windows: per stream, serially over its runs. win[r] (32 KiB) = the 32 KiB of final bytes that precede run r + 1, i.e.
+// the last 32 KiB up to the end of run r (zero-filled where the stream is shorter; such positions are never referenced by a
+// valid stream — a marker that points there is reported through `bad`).
+struct RunStream {
+    uint32_t first_run, n_runs;  // runs [first_run, first_run + n_runs) of the launch belong to this stream, in order
+};
+
+// run_off[n_runs + 1]: the runs' offsets in the launch's compact symbol space (run r = sym[run_off[r], run_off[r + 1])).
+#define CZK_WINDOW_SMEM 65536
+__global__ void __launch_bounds__(1024) inflate_window_kernel(const RunStream *streams, const uint64_t *run_off, const uint16_t *sym,
+                                                              uint8_t *win, uint32_t *bad) {
+    CZ_DYNAMIC_SMEM(smem_raw);
+    uint8_t (*W)[32768] = (uint8_t (*)[32768])smem_raw;
+    const RunStream rs = streams[blockIdx.x];
+    const uint32_t tid = threadIdx.x;
+    const uint64_t stream_start = run_off[rs.first_run];
+    int cur = 0;
+    uint32_t my_bad = 0;
+    for (uint32_t k = 0; k < rs.n_runs; k++) {
+        const uint32_t r = rs.first_run + k;
+        const uint64_t a = run_off[r], e = run_off[r + 1], len = e - a;
+        const uint8_t *Wp = W[cur];
+        uint8_t *Wn = W[cur ^ 1];
+        const uint64_t valid_before = a - stream_start;  // bytes of the stream in front of this run
+        for (uint32_t j = tid; j < 32768; j += 1024) {
+            // window position j <-> stream position e - 32768 + j
+            uint32_t v = 0;
+            if (len + j >= 32768) {  // inside this run
+                const uint64_t idx = len + j - 32768;
+                const uint32_t s = sym[a + idx];
+                if (s & CZK_MARK) {
+                    const uint32_t w = s & 0x7fffu;
+                    if (32768u - w > valid_before) my_bad = 1;  // reaches before the start of the stream
+                    else v = Wp[w];
+                } else v = s;
+            } else {  // still in front of this run: carried over from the previous window
+                const uint32_t w = (uint32_t)(j + len);
+                v = (k == 0) ? 0u : Wp[w];
+            }
+            Wn[j] = (uint8_t)v;
+        }
+        __syncthreads();
+        uint4 *dst = (uint4 *)(win + (uint64_t)r * 32768);
+        const uint4 *srcv = (const uint4 *)Wn;
+        for (uint32_t j = tid; j < 2048; j += 1024) dst[j] = srcv[j];
+        cur ^= 1;
+        __syncthreads();
+    }
+    if (my_bad) atomicOr(bad, 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 5. symbols -> bytes. One CTA per (run, 64 KiB slice): the window in front of the run in shared memory. Run r's symbols are
+// sym[run_off[r], run_off[r + 1]) and its bytes go to out[final_off[r] ...). Checks per run are computed afterwards from the bytes.
+struct RunSlice {
+    uint32_t run;      // run index in the launch
+    uint32_t slice;    // 64 KiB slice of the run
+};
+__global__ void __launch_bounds__(256) inflate_resolve_kernel(const RunSlice *slices, uint32_t n_slices, const uint64_t *run_off,
+                                                              const uint64_t *final_off, const uint8_t *run_is_first, const uint16_t *sym,
+                                                              const uint8_t *win, uint8_t *out, uint32_t *bad) {
+    __shared__ __align__(16) uint8_t W[32768];
+    const uint32_t sl = blockIdx.x;
+    if (sl >= n_slices) return;
+    const uint32_t r = slices[sl].run;
+    const uint64_t a = run_off[r], e = run_off[r + 1];
+    const uint64_t lo = a + (uint64_t)slices[sl].slice * 65536;
+    const uint64_t hi = lo + 65536 < e ? lo + 65536 : e;
+    const bool first = run_is_first[r] != 0;
+    if (!first) {
+        const uint4 *srcv = (const uint4 *)(win + (uint64_t)(r - 1) * 32768);
+        uint4 *dstv = (uint4 *)W;
+        for (uint32_t j = threadIdx.x; j < 2048; j += 256) dstv[j] = srcv[j];
+    }
+    __syncthreads();
+    uint8_t *ob = out + final_off[r];
+    uint32_t my_bad = 0;
+    for (uint64_t p = lo + threadIdx.x; p < hi; p += 256) {
+        const uint32_t s = sym[p];
+        uint32_t v = s;
+        if (s & CZK_MARK) {
+            if (first) { my_bad = 1; v = 0; }  // nothing precedes the first run of a stream
+            else v = W[s & 0x7fffu];
+        }
+        ob[p - a] = (uint8_t)v;
+    }
+    if (my_bad) atomicOr(bad, 1u);
+}
+
+// Adler-32 and CRC-32 of every run's final bytes: one warp per run. checks[2r] = adler (seed 1), checks[2r+1] = crc (seed 0).
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) inflate_run_check_kernel(const uint64_t *run_off, const uint64_t *final_off, uint32_t n_runs,
+                                                                       const uint8_t *out, const CrcTables *crc, int check_kind, uint32_t *checks) {
+    __shared__ uint32_t crc_tab[256 + 34];
+    for (uint32_t i = threadIdx.x; i < 256 + 34; i += WARPS * 32) crc_tab[i] = i < 256 ? crc->table[i] : crc->pow128[i - 256];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (r >= n_runs) return;
+    const uint64_t a = final_off[r], e = a + (run_off[r + 1] - run_off[r]);
+    uint32_t adler = 1, c = 0;
+    if (check_kind & 1)
+        for (uint64_t p = a; p < e; p += 8192) adler = warp_adler32(adler, out + p, (uint32_t)(e - p < 8192 ? e - p : 8192), lane);
+    if (check_kind & 2) {
+        uint64_t p = a;
+        while (e - p >= 128) {
+            uint32_t q = (uint32_t)((e - p) >> 7);
+            if (q > 32) q = 32;
+            c = warp_crc32_pieces(c, out + p, q, crc_tab, crc_tab + 256, lane);
+            p += (uint64_t)q * 128;
+        }
+        if (p < e) {
+            uint32_t c2 = 0;
+            if (lane == 0) c2 = crc32_serial(c, out + p, (uint32_t)(e - p), crc_tab);
+            c = __shfl_sync(CZK_FULL, c2, 0);
+        }
+    }
+    if (lane == 0) { checks[2 * r] = adler; checks[2 * r + 1] = c; }
+}
+
+}  // namespace czk

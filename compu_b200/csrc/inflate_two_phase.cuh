@@ -39,6 +39,24 @@ struct TokMeta {
     uint32_t wrap;       // 0 raw, 1 zlib (Adler-32), 2 gzip (CRC-32)
 };
 
+// RUN mode (block-parallel decode of long streams, inflate_runs.cuh): a unit of phase A is a RUN — a range of ONE stream's
+// blocks that starts at a block boundary found by the candidate search (or at the start of the stream) and stops at the first
+// block boundary at or after its target (where the next run starts). All runs of a stream share the stream's input range, so
+// bit positions are relative to the start of the stream.
+struct RunDesc {
+    uint64_t in_lo, in_hi; // the STREAM's input: bytes [in_lo, in_hi) of the launch's input buffer (shared by all its runs)
+    uint64_t start_bit;   // first bit of the run's first block header (run 0 of a stream: 0, the container header comes first)
+    uint64_t target_bit;  // stop at the first block boundary >= this (UINT64_MAX: run to the end of the stream)
+    uint32_t mid_stream;  // 1: starts at a block header inside the stream (no container header, distances may reach before the run)
+    uint32_t pad;
+};
+struct RunResult {
+    uint64_t end_bit;     // where the run stopped (a block boundary, or the end of the final block)
+    uint32_t final_block; // 1: the run ended with the stream's final block
+    uint32_t pad;
+};
+#define CZK_ST_RUN_END 4  // phase A, run mode: stopped at the target boundary (internal status, never reaches the caller)
+
 struct TwoPhaseParams {
     InflateParams base;          // base.counter: phase A work counter
     uint32_t *tok;               // token area: unit u starts at word tok_word_off(out_off[u] - out_off[0], u)
@@ -48,6 +66,8 @@ struct TwoPhaseParams {
     unsigned long long *counter_c;  // work counter of inflate_lz_cta_kernel, zero before launch
     uint32_t cta_tile;           // != 0: units whose output slot is at most this many bytes belong to inflate_lz_cta_kernel
     uint32_t spin_ns;            // inflate_lz_cta_kernel: back-off of a warp that found no ready token
+    const RunDesc *runs;         // != null: run mode, one RunDesc per unit
+    RunResult *run_res;          // run mode: per unit
 };
 
 __host__ __device__ inline uint64_t tok_word_off(uint64_t out_off, uint64_t unit) { return out_off + 8 * unit; }
@@ -90,6 +110,8 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
     uint32_t lit = 0, nlit = 0;               // pending literal bytes (at most 2 between tokens)
     int result = 0, wrap = 0;
     uint32_t bfinal = 0, nlit_sym = 0, ndist_sym = 0, stored_len = 0, expect = 0;
+    uint64_t run_start = 0, run_target = ~0ull;  // run mode
+    bool run_mid = false;
 
     const bool emit = !Q.count_only;
 #define CZK_PUT(x) do { if (emit) *tp++ = (x); } while (0)
@@ -102,13 +124,26 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
             if (u >= P.n) st = SS_EXIT;
             else {
                 unit = P.ids ? P.ids[u] : (uint32_t)u;
-                uint64_t i0 = P.in_off[unit], i1 = P.in_off[unit + 1], o0 = P.out_off[unit], o1 = P.out_off[unit + 1];
+                uint64_t i0, i1;
+                if (Q.runs) { i0 = Q.runs[unit].in_lo; i1 = Q.runs[unit].in_hi; }
+                else { i0 = P.in_off[unit]; i1 = P.in_off[unit + 1]; }
+                const uint64_t o0 = P.out_off[unit], o1 = P.out_off[unit + 1];
                 in_base = P.in + i0; in_len = i1 - i0;
                 cap = o1 - o0; pos = 0;
                 tp0 = tp = emit ? Q.tok + tok_word_off(o0 - P.out_off[0], unit) : nullptr;
                 lit = 0; nlit = 0; bfinal = 0; result = 0; expect = 0;
                 br.init(in_base, in_len);
                 st = SS_HEADER;
+                if (Q.runs) {
+                    const RunDesc rd = Q.runs[unit];
+                    run_start = rd.start_bit; run_target = rd.target_bit; run_mid = rd.mid_stream != 0;
+                    if (run_mid) {
+                        br.seek(run_start >> 3);
+                        br.skip((uint32_t)(run_start & 7));
+                        wrap = 0;
+                        st = SS_BLOCK;
+                    }
+                }
             }
         }
         if (__all_sync(CZK_FULL, st == SS_EXIT)) break;
@@ -135,6 +170,9 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
             if (P.segment_mode && br.consumed() >= br.total) {
                 result = br.consumed() == br.total ? ST_FINISHED : ST_NEED_INPUT;
                 st = SS_TRAILER;
+            } else if (Q.runs && br.consumed() >= run_target && br.consumed() > run_start) {
+                result = CZK_ST_RUN_END;  // the next run starts at (or before) this boundary
+                st = SS_FINISH;
             } else {
                 br.refill();
                 bfinal = br.get(1);
@@ -246,7 +284,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
                     if (pos >= cap) { result = br.out_full_status(); st = SS_FINISH; break; }
                     if (pos + n > cap) n = (uint32_t)(cap - pos);
                 }
-                if ((uint64_t)dist > pos) { result = ST_E_DATA; st = SS_FINISH; break; }
+                if ((uint64_t)dist > pos && !run_mid) { result = ST_E_DATA; st = SS_FINISH; break; }
                 CZK_FLUSH_LIT();
                 CZK_PUT(n | (dist << 9));
                 pos += n;
@@ -281,7 +319,9 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
 
         // ---- (7) trailer: the check value is compared by phase B, the length check happens here
         if (st == SS_TRAILER) {
-            if (!P.segment_mode && result == ST_FINISHED) {
+            if (Q.runs) {
+                // the container trailer of a stream decoded in runs is checked by the host: it needs all runs' lengths and checks
+            } else if (!P.segment_mode && result == ST_FINISHED) {
                 br.skip((uint32_t)((0 - br.consumed()) & 7));
                 if (wrap == 1) {
                     uint32_t t = 0;
@@ -315,6 +355,13 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
             m.expect = expect;
             m.wrap = (uint32_t)wrap;
             Q.meta[unit] = m;
+            if (Q.runs) {
+                RunResult rr;
+                rr.end_bit = br.consumed();
+                rr.final_block = result == ST_FINISHED ? 1u : 0u;
+                rr.pad = 0;
+                Q.run_res[unit] = rr;
+            }
             if (P.in_consumed) {
                 uint64_t c = (br.consumed() + 7) >> 3;
                 P.in_consumed[unit] = c < in_len ? c : in_len;

@@ -188,9 +188,11 @@ int cz_deflate_segments_device(void *cuda_stream, size_t n, const uint8_t *d_in,
 uint32_t cz_adler32_combine(uint32_t adler1, uint32_t adler2, uint64_t len2);
 uint32_t cz_crc32_combine(uint32_t crc1, uint32_t crc2, uint64_t len2);
 
-/* Long single streams (>= 2 MiB compressed) given to the inflate entry points are split speculatively at full-flush markers
-   and decoded in parallel when every piece verifies (compu_b200/csrc/host.cu); otherwise they take the serial path. Counters
-   since load: units the split was tried on / units decoded by it. */
+/* Long streams (>= 128 KiB compressed) given to the inflate entry points are cut into runs of blocks — at block headers found
+   by a candidate search, whoever produced the stream, flush points or not — and the runs are decoded in parallel
+   (compu_b200/csrc/inflate_runs.cuh); what that path cannot prove correct (data errors, truncation, slots that are too small)
+   takes the serial kernels, which reproduce zlib's partial output and status. Counters since load: long units seen / long
+   units decoded by the parallel path. */
 void cz_split_stats(uint64_t *tried, uint64_t *split);
 
 /* The multi-GPU partitioner used by the batched entry points: cuts n packed units (offsets[n+1]) into `parts`

@@ -5,6 +5,7 @@
 #include "../../compu_b200/csrc/inflate_lc_kernel.cuh"
 #include "../../compu_b200/csrc/inflate_two_phase.cuh"
 #include "../../compu_b200/csrc/deflate_kernels.cuh"
+#include "../../compu_b200/csrc/inflate_runs_host.h"
 
 using namespace czk;
 
@@ -84,6 +85,92 @@ extern "C" int sim_inflate_resume(const uint8_t *in, uint64_t in_len, uint8_t *s
     return 0;
 }
 extern "C" uint64_t sim_resume_state_bytes() { return sizeof(ResumeState); }
+
+// The block-parallel path for long streams (inflate_runs.cuh) with the product's own host orchestration
+// (inflate_runs_host.h) on an emulator backend: "device" memory is host memory, launches are cusim launches.
+struct SimRunsBackend {
+    uint8_t *in, *out;
+    std::vector<uint8_t> arena;
+    size_t used = 0;
+    CrcTables crc_tab;
+    unsigned grid;
+    uint64_t seed;
+    SimRunsBackend() { init_crc_tables(&crc_tab); arena.resize(64u << 20); }
+    uint8_t *d_in() { return in; }
+    uint8_t *d_out() { return out; }
+    void scratch_reset() { used = 0; }
+    bool scratch_need(size_t total) { if (total > arena.size()) arena.resize(total); return true; }
+    bool out_need(size_t bytes) { out_store.assign(bytes, 0xEE); out = out_store.data(); return true; }
+    std::vector<uint8_t> out_store;
+    void *scratch(size_t bytes) {
+        const size_t a = (used + 255) & ~(size_t)255;
+        if (a + bytes + 256 > arena.size()) return nullptr;
+        used = a + bytes;
+        memset(arena.data() + a, 0xCD, bytes);  // scratch is NOT zeroed on the device either
+        return arena.data() + a;
+    }
+    bool h2d(void *d, const void *h, size_t n) { memcpy(d, h, n); return true; }
+    bool d2h(void *h, const void *d, size_t n) { memcpy(h, d, n); return true; }
+    bool zero(void *d, size_t n) { memset(d, 0, n); return true; }
+    const CrcTables *crc() { return &crc_tab; }
+    bool candidates(const CandChunk *c, uint32_t n, uint64_t *cand) {
+        cusim::set_seed(seed++);
+        cusim::launch((n + 3) / 4, 128, 0, inflate_candidates_kernel, (const uint8_t *)in, c, n, cand);
+        return true;
+    }
+    bool tok(const TwoPhaseParams &Q) {
+        cusim::set_seed(seed++);
+        cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2>, Q);
+        return true;
+    }
+    bool lz16(const TwoPhaseParams &Q, uint16_t *sym) {
+        cusim::set_seed(seed++);
+        cusim::launch(grid, 2 * 32, 0, inflate_lz16_kernel<2>, Q, sym);
+        return true;
+    }
+    bool window(const RunStream *st, uint32_t ns, const uint64_t *run_off, const uint16_t *sym, uint8_t *win, uint32_t *bad) {
+        if (!ns) return true;
+        cusim::set_seed(seed++);
+        cusim::launch(ns, 1024, CZK_WINDOW_SMEM, inflate_window_kernel, st, run_off, sym, win, bad);
+        return true;
+    }
+    bool resolve(const RunSlice *sl, uint32_t nsl, const uint64_t *run_off, const uint64_t *final_off, const uint8_t *first,
+                 const uint16_t *sym, const uint8_t *win, uint8_t *o, uint32_t *bad) {
+        if (!nsl) return true;
+        cusim::set_seed(seed++);
+        cusim::launch(nsl, 256, 0, inflate_resolve_kernel, sl, nsl, run_off, final_off, first, sym, win, o, bad);
+        return true;
+    }
+    bool check(const uint64_t *run_off, const uint64_t *final_off, uint32_t n, const uint8_t *o, int kind, uint32_t *checks) {
+        cusim::set_seed(seed++);
+        cusim::launch((n + 1) / 2, 2 * 32, 0, inflate_run_check_kernel<2>, run_off, final_off, n, o, (const CrcTables *)&crc_tab, kind, checks);
+        return true;
+    }
+};
+
+// n long streams, packed like sim_inflate. ok[i] = 1: decoded by the parallel path (out_lens / consumed valid); 0: left to the
+// serial path. n_runs[i] = runs the stream was cut into.
+extern "C" int sim_inflate_runs(size_t n, uint8_t *in, const uint64_t *in_off, uint8_t *out, const uint64_t *out_off, uint64_t *out_lens,
+                                uint64_t *consumed, uint8_t *ok, uint32_t *n_runs, int window_bits, uint64_t chunk_bytes, int grid,
+                                uint64_t seed) {
+    static SimRunsBackend bk;
+    bk.in = in; bk.out = nullptr; bk.grid = (unsigned)grid; bk.seed = seed;
+    std::vector<czh::BigUnit> units(n);
+    for (size_t i = 0; i < n; i++) {
+        units[i].h_in = in + in_off[i]; units[i].in_len = in_off[i + 1] - in_off[i]; units[i].d_in_lo = in_off[i];
+        units[i].out_cap = out_off[i + 1] - out_off[i]; units[i].window_bits = window_bits;
+    }
+    int rc = czh::inflate_runs_batch(bk, units, chunk_bytes);
+    for (size_t i = 0; i < n; i++) {
+        ok[i] = units[i].ok; out_lens[i] = units[i].out_len; consumed[i] = units[i].in_consumed; n_runs[i] = units[i].n_runs;
+        if (units[i].ok) {
+            memcpy(out + out_off[i], bk.out + units[i].d_out_off, units[i].out_len);
+            // nothing may be written between the units of the device output buffer
+            for (uint64_t k = units[i].out_len; k < units[i].out_len + 16; k++) if (bk.out[units[i].d_out_off + k] != 0xEE) return -3;
+        }
+    }
+    return rc;
+}
 
 extern "C" uint32_t sim_crc32_combine(uint32_t a, uint32_t b, uint64_t len2) { return crc32_combine_u(a, b, len2); }
 extern "C" uint32_t sim_adler32_combine(uint32_t a, uint32_t b, uint64_t len2) { return adler32_combine_u(a, b, len2); }

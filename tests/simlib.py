@@ -88,3 +88,26 @@ def sim_deflate(units, seg_bytes=65536, level=6, strategy=0, window_bits=15, pie
         o = int(pos[i]) if packed else int(out_off[i])
         streams.append(bytes(out[o:o + int(out_len[i])]) if status[i] == 2 else b"")
     return streams, status, out_len, checks, seg_sizes
+
+
+def sim_inflate_runs(streams, caps, window_bits, chunk_bytes=4096, grid=3, seed=1):
+    """The block-parallel path for long streams (inflate_runs.cuh + inflate_runs_host.h) on the emulator.
+    Returns (outputs, ok[], out_lens, consumed, n_runs)."""
+    L = lib()
+    n = len(streams)
+    inbuf, in_off = pack(streams)
+    inbuf = np.concatenate([inbuf, np.full(64, 0xA5, dtype=np.uint8)])
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    out_off[1:] = np.cumsum(caps)
+    out = np.full(int(out_off[-1]) + 64, 0xEE, dtype=np.uint8)
+    out_lens = np.zeros(n, dtype=np.uint64)
+    consumed = np.zeros(n, dtype=np.uint64)
+    ok = np.zeros(n, dtype=np.uint8)
+    nruns = np.zeros(n, dtype=np.uint32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    r = L.sim_inflate_runs(ctypes.c_size_t(n), p(inbuf), p(in_off), p(out), p(out_off), p(out_lens), p(consumed), p(ok), p(nruns),
+                           window_bits, ctypes.c_uint64(chunk_bytes), grid, ctypes.c_uint64(seed))
+    assert r == 0
+    assert (out[int(out_off[-1]):] == 0xEE).all()
+    outs = [bytes(out[int(out_off[i]):int(out_off[i]) + int(out_lens[i])]) if ok[i] else None for i in range(n)]
+    return outs, ok, out_lens, consumed, nruns
