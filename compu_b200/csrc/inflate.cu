@@ -2,6 +2,8 @@
 // (cz_inflate_batch_device / cz_inflate_segments_device, include/compu_b200.h).
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "host_common.h"
 #include "inflate_kernel.cuh"
 #include "inflate_lane_kernel.cuh"
@@ -105,6 +107,7 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
         return CZ_E_MEM;
     }
     czk::TwoPhaseParams Q;
+    memset(&Q, 0, sizeof Q);
     Q.base = P;
     Q.count_only = 0;
     Q.counter_b = (unsigned long long *)((uint8_t *)d_ws + 128);
@@ -230,10 +233,14 @@ struct CudaRunsBackend {
         ctx = c;
         if (!st && !CZ_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking))) return false;
         if (!configured) {
-            auto ka = czk::inflate_tok_kernel<14>;
-            auto kl = czk::inflate_tok_kernel<4>;
+            auto ka = czk::inflate_tok_kernel<14, true>;
+            auto kl = czk::inflate_tok_kernel<4, true>;
+            auto kac = czk::inflate_tok_kernel<14, false>;
+            auto klc = czk::inflate_tok_kernel<4, false>;
             if (!CZ_CUDA(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)czk::inflate_tok_smem_bytes<14>())) ||
                 !CZ_CUDA(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)czk::inflate_tok_smem_bytes<4>())) ||
+                !CZ_CUDA(cudaFuncSetAttribute(kac, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)czk::inflate_tok_smem_bytes<14>())) ||
+                !CZ_CUDA(cudaFuncSetAttribute(klc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)czk::inflate_tok_smem_bytes<4>())) ||
                 !CZ_CUDA(cudaFuncSetAttribute(czk::inflate_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CZK_WINDOW_SMEM)) ||
                 !CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_tok, ka, 14 * 32, czk::inflate_tok_smem_bytes<14>())) ||
                 !CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_lz16, czk::inflate_lz16_kernel<8>, 256, 0))) return false;
@@ -265,11 +272,14 @@ struct CudaRunsBackend {
     bool tok(const czk::TwoPhaseParams &Q) {
         const uint32_t n = Q.base.n;
         // few runs: 4 warps per CTA spread over the SMs (a lane decodes sooner when its warp shares the schedulers with 3 others)
-        if (n <= (uint32_t)ctx->sm_count * 32 * 4 * 2) CZ_KL(czk::inflate_tok_kernel<4><<<(n + 127) / 128, 128, czk::inflate_tok_smem_bytes<4>(), st>>>(Q));
-        else {
+        if (n <= (uint32_t)ctx->sm_count * 32 * 4 * 2) {
+            if (Q.count_only) CZ_KL(czk::inflate_tok_kernel<4, false><<<(n + 127) / 128, 128, czk::inflate_tok_smem_bytes<4>(), st>>>(Q));
+            else CZ_KL(czk::inflate_tok_kernel<4, true><<<(n + 127) / 128, 128, czk::inflate_tok_smem_bytes<4>(), st>>>(Q));
+        } else {
             uint64_t g = (n + 32 * 14 - 1) / (32 * 14), gmax = (uint64_t)ctx->sm_count * per_sm_tok;
             if (g > gmax) g = gmax;
-            CZ_KL(czk::inflate_tok_kernel<14><<<(unsigned)g, 14 * 32, czk::inflate_tok_smem_bytes<14>(), st>>>(Q));
+            if (Q.count_only) CZ_KL(czk::inflate_tok_kernel<14, false><<<(unsigned)g, 14 * 32, czk::inflate_tok_smem_bytes<14>(), st>>>(Q));
+            else CZ_KL(czk::inflate_tok_kernel<14, true><<<(unsigned)g, 14 * 32, czk::inflate_tok_smem_bytes<14>(), st>>>(Q));
         }
         return ok();
     }
@@ -297,10 +307,10 @@ struct CudaRunsBackend {
 };
 
 static uint64_t runs_chunk_bytes() {
-    static const uint64_t v = [] { const char *e = getenv("CZ_RUN_CHUNK_KB"); long k = e ? atol(e) : 0; return k >= 4 ? (uint64_t)k << 10 : (uint64_t)(64u << 10); }();
+    static const uint64_t v = [] { const char *e = getenv("CZ_RUN_CHUNK_KB"); long k = e ? atol(e) : 0; return k >= 4 ? (uint64_t)k << 10 : (uint64_t)(32u << 10); }();
     return v;
 }
-uint64_t runs_min_unit_bytes() { return 2 * runs_chunk_bytes(); }
+uint64_t runs_min_unit_bytes() { return std::max<uint64_t>(128u << 10, 2 * runs_chunk_bytes()); }
 
 // Decodes the long streams `ids` of a packed host batch on device `dev` with the block-parallel path, in batches bounded by
 // device memory. done[i] = 1 for the units it decoded (out, out_lens, statuses = Finished, in_consumed written); the others

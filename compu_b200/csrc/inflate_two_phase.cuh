@@ -80,7 +80,8 @@ __host__ __device__ inline uint64_t tok_word_off(uint64_t out_off, uint64_t unit
 #endif
 #define CZK_LZ_SHORT 12  // phase B (token-parallel): matches up to this long are copied by their own lane (8/12/16/24/32 measured: 33.9/32.6/34.0/35.5/38.0 ms)
 
-template <int WARPS>
+// EMIT = false: counting only (no token is written; sizes, statuses and end positions are the result).
+template <int WARPS, bool EMIT = true>
 __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams Q) {
     const InflateParams &P = Q.base;
     CZ_DYNAMIC_SMEM(smem_raw);
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
     uint64_t run_start = 0, run_target = ~0ull;  // run mode
     bool run_mid = false;
 
-    const bool emit = !Q.count_only;
+    constexpr bool emit = EMIT;
 #define CZK_PUT(x) do { if (emit) *tp++ = (x); } while (0)
 #define CZK_FLUSH_LIT() do { if (nlit) { CZK_PUT(CZK_TOK_LIT | (nlit << 24) | lit); lit = 0; nlit = 0; } } while (0)
 
@@ -225,6 +226,76 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
         if (st == SS_DECODE) {
             int budget = CZK_LC_BUDGET;
             const int64_t pos_safe = (int64_t)cap - 258;
+            // ---- fast loop. While three more input words and 258 bytes of capacity remain, none of the end-of-input /
+            // end-of-slot conditions can occur (one symbol takes at most 48 bits and 258 bytes): no masking of the unit's
+            // last word, no overrun tests, 32-bit position arithmetic, and the only exits are the ones below. Everything
+            // unusual — the last words of the input, the end of the slot, end of block, an invalid code — is left untouched
+            // for the general loop that follows (the symbol is not consumed here).
+            if ((int64_t)pos <= pos_safe) {
+                uint64_t buf = br.buf;
+                uint32_t cnt = br.cnt, widx = br.widx, nextw = br.nextw, nextw2 = br.nextw2;
+                const uint32_t wend = br.wend;
+                const uint32_t *const words = br.words;
+                const uint64_t room64 = (uint64_t)(pos_safe - (int64_t)pos);
+                const uint32_t room = room64 > 0x7fff0000u ? 0x7fff0000u : (uint32_t)room64;  // symbols may START while adv <= room
+                const uint32_t reach = pos >= 32768u || run_mid ? 32768u : (uint32_t)pos;     // distances up to reach + adv are valid
+                uint32_t adv = 0;
+                while (budget > 0 && widx + 3 <= wend && adv <= room) {
+                    if (cnt <= 32) {
+                        buf |= (uint64_t)nextw << cnt;
+                        cnt += 32;
+                        widx++;
+                        nextw = nextw2;
+                        nextw2 = widx + 1 < wend ? __ldg(words + widx + 1) : 0u;
+                    }
+                    uint32_t v = __brev((uint32_t)buf) >> 16;
+                    const uint32_t cl = lc_code_len(v, llim);
+                    if (cl > 15) break;
+                    const uint32_t info = my.lit_info[cl];
+                    const uint32_t idx = ((v >> (16 - cl)) + info) & 0xffffu;
+                    const uint32_t sym = my.lit_sorted[idx < 288 ? idx : 287] | (idx >= (info >> 16) ? 256u : 0u);
+                    if (sym < 256) {  // literal
+                        buf >>= cl; cnt -= cl;
+                        adv++;
+                        lit |= sym << (8 * nlit);
+                        if (++nlit == 3) { CZK_PUT(CZK_TOK_LIT | (3u << 24) | lit); lit = 0; nlit = 0; }
+                        budget--;
+                        continue;
+                    }
+                    if (sym == 256 || sym > 285) break;  // end of block / invalid: the general loop decodes it again
+                    // length + distance; the bit reader is only committed once the whole pair is known to be valid
+                    uint64_t b2 = buf >> cl;
+                    uint32_t c2 = cnt - cl, w2 = widx, n1 = nextw, n2 = nextw2;
+                    const uint32_t li = len_info[sym - 257];
+                    const uint32_t eb = li >> 9;
+                    const uint32_t len = (li & 0x1ff) + ((uint32_t)b2 & ((1u << eb) - 1u));
+                    b2 >>= eb; c2 -= eb;
+                    if (c2 <= 32) {
+                        b2 |= (uint64_t)n1 << c2;
+                        c2 += 32;
+                        w2++;
+                        n1 = n2;
+                        n2 = w2 + 1 < wend ? __ldg(words + w2 + 1) : 0u;
+                    }
+                    v = __brev((uint32_t)b2) >> 16;
+                    const uint32_t dcl = lc_code_len(v, dlim);
+                    if (dcl > 15) break;
+                    const uint32_t dsym = my.dist_sorted[((v >> (16 - dcl)) + my.dist_base[dcl]) & 31];
+                    if (dsym > 29) break;
+                    b2 >>= dcl; c2 -= dcl;
+                    const uint32_t deb = dsym < 2 ? 0 : (dsym >> 1) - 1;
+                    const uint32_t dist = ((dsym < 2 ? dsym : 2 + (dsym & 1)) << deb) + 1 + ((uint32_t)b2 & ((1u << deb) - 1u));
+                    b2 >>= deb; c2 -= deb;
+                    if (dist > reach + adv) break;  // "invalid distance too far back": reported by the general loop
+                    buf = b2; cnt = c2; widx = w2; nextw = n1; nextw2 = n2;
+                    CZK_FLUSH_LIT();
+                    CZK_PUT(len | (dist << 9));
+                    adv += len;
+                    budget--;
+                }
+                br.buf = buf; br.cnt = cnt; br.widx = widx; br.nextw = nextw; br.nextw2 = nextw2;
+                pos += adv;
+            }
             while (budget-- > 0) {
                 br.refill();
                 const bool slow = !(br.widx + 3 <= br.wend && (int64_t)pos <= pos_safe);

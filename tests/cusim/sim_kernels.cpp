@@ -44,6 +44,7 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
             std::vector<TokMeta> meta(n);
             unsigned long long counter_b = 0, counter_c = 0;
             TwoPhaseParams Q;
+            memset(&Q, 0, sizeof Q);
             Q.base = P; Q.tok = tok.data(); Q.meta = meta.data(); Q.counter_b = &counter_b; Q.count_only = 0;
             Q.counter_c = &counter_c; Q.cta_tile = D == -4 ? CZK_LZ_TILE : 0; Q.spin_ns = 0;
             cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2>, Q);
@@ -120,7 +121,8 @@ struct SimRunsBackend {
     }
     bool tok(const TwoPhaseParams &Q) {
         cusim::set_seed(seed++);
-        cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2>, Q);
+        if (Q.count_only) cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2, false>, Q);
+        else cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2, true>, Q);
         return true;
     }
     bool lz16(const TwoPhaseParams &Q, uint16_t *sym) {
