@@ -137,6 +137,12 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
     P.blk_end = (uint32_t *)(ws + w.blk_end); P.freqs = (uint32_t *)(ws + w.freqs); P.plans = (BlockPlan *)(ws + w.plans);
     P.crc = ctx->d_crc;
     P.tune = czk::deflate_tuning(L.level, L.strategy);
+    {   // experiment knob (tools/sweep_deflate_ratio.py picks, measured on the GPU with these): CZ_DEFLATE_CHAIN / CZ_DEFLATE_NICE
+        static const int ov_chain = [] { const char *e = getenv("CZ_DEFLATE_CHAIN"); return e ? atoi(e) : 0; }();
+        static const int ov_nice = [] { const char *e = getenv("CZ_DEFLATE_NICE"); return e ? atoi(e) : 0; }();
+        if (ov_chain > 0 && P.tune.max_chain) P.tune.max_chain = (uint32_t)ov_chain;
+        if (ov_nice > 0 && P.tune.max_chain) P.tune.nice_len = (uint32_t)ov_nice;
+    }
     P.window_bits = L.window_bits; P.level = L.level; P.piece_mode = L.piece_mode; P.check_kind = L.check_kind;
     if (!L.piece_mode && L.window_bits != -15 && !L.d_unit_checks) { set_error("zlib/gzip framing needs the checks array"); return CZ_E_STREAM; }
     if (L.d_unit_out_pos_ret) *L.d_unit_out_pos_ret = P.unit_out_pos;

@@ -35,8 +35,10 @@ __host__ __device__ inline DeflateTuning deflate_tuning(int level, int strategy)
     if (level < 0) level = 6;
     if (level > 9) level = 9;
     // chain depth / nice length per level, shaped after zlib's configuration_table (deflate.c)
-    // (level 6: chain 16 / nice 64 measures +0.3 % / +1.2 % of zlib 1.3 level 6 on Markov text / alice29.txt)
-    const uint32_t chain[10] = {0, 2, 3, 4, 6, 10, 16, 24, 48, 128};
+    // Level 6 is the benchmarked level: (chain, nice) swept with tools/sweep_deflate_ratio.py (size against zlib 1.3 level 6) and
+    // timed on a B200 (profiles/r2_notes.md): chain 16 / 12 / 10 / 8 -> 91.9 / 84.1 / 79.8 / 75.2 ms per GiB at 1.005 / 1.010 /
+    // 1.013 / 1.018 x zlib's size on Markov text; 10 is the fastest point within 1.5 % on all three synthetic classes.
+    const uint32_t chain[10] = {0, 2, 3, 4, 6, 8, 10, 24, 48, 128};
     const uint32_t nice[10] = {0, 8, 16, 32, 16, 32, 64, 128, 258, 258};
     t.max_chain = chain[level];
     t.nice_len = nice[level];

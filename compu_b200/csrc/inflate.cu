@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "host_common.h"
 #include "inflate_kernel.cuh"
@@ -265,6 +266,16 @@ struct CudaRunsBackend {
     bool zero(void *d, size_t n) { return CZ_CUDA(cudaMemsetAsync(d, 0, n, st)); }
     const czk::CrcTables *crc() { return ctx->d_crc; }
     bool ok() { return CZ_CUDA(cudaGetLastError()); }
+    // CZ_TRACE=1: host wall-clock timeline of the phases (each mark waits for the stream: tracing serialises, timing does not)
+    std::chrono::steady_clock::time_point t_last;
+    void mark(const char *phase) {
+        static const bool tracing = getenv("CZ_TRACE") != nullptr;
+        if (!tracing) return;
+        cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        if (strcmp(phase, "start")) fprintf(stderr, "[cz] runs: %-14s %8.2f ms\n", phase, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    }
     bool candidates(const czk::CandChunk *c, uint32_t n, uint64_t *cand) {
         CZ_KL(czk::inflate_candidates_kernel<<<(n + 3) / 4, 128, 0, st>>>(d_in(), c, n, cand));
         return ok();
@@ -335,7 +346,8 @@ int inflate_long_units(int dev, const std::vector<size_t> &ids, const uint8_t *i
         uint64_t in_bytes = 0, cap_bytes = 0;
         while (b < ids.size()) {
             const uint64_t il = in_off[ids[b] + 1] - in_off[ids[b]], ol = out_off[ids[b] + 1] - out_off[ids[b]];
-            if (b > a && (in_bytes + il > batch_in || cap_bytes + ol > batch_out)) break;
+            if (b > a && (in_bytes + il > batch_in || cap_bytes + ol > batch_out ||
+                          out_off[ids[b] + 1] - out_off[ids[a]] > 2 * batch_out)) break;  // (the device buffer mirrors the callers' span)
             in_bytes += runs_align(il + 64); cap_bytes += ol;
             b++;
         }
@@ -348,20 +360,32 @@ int inflate_long_units(int dev, const std::vector<size_t> &ids, const uint8_t *i
             const size_t i = ids[k];
             U.h_in = in + in_off[i]; U.in_len = in_off[i + 1] - in_off[i]; U.d_in_lo = o;
             U.out_cap = out_off[i + 1] - out_off[i]; U.window_bits = window_bits;
+            U.d_out_off = out_off[i] - out_off[ids[a]];  // the caller's layout, so that neighbouring units leave in one copy
             copied = copied && CZ_CUDA(cudaMemcpyAsync(bk->d_in() + o, U.h_in, U.in_len, cudaMemcpyHostToDevice, bk->st));
             o += runs_align(U.in_len + 64);
         }
+        bk->mark("start");
         if (!copied || !CZ_CUDA(cudaStreamSynchronize(bk->st))) return CZ_E_MEM;
+        bk->mark("h2d");
         const int rc = inflate_runs_batch(*bk, units, runs_chunk_bytes());
         if (rc == 0) {
             bool ok = true;
-            for (size_t k = a; k < b; k++) {
-                const BigUnit &U = units[k - a];
-                if (!U.ok) continue;
-                const size_t i = ids[k];
-                if (U.out_len) ok = ok && CZ_CUDA(cudaMemcpyAsync(out + out_off[i], bk->d_out() + U.d_out_off, U.out_len, cudaMemcpyDeviceToHost, bk->st));
+            // device -> host: consecutive decoded units whose slots are exactly full and adjacent leave in one copy
+            size_t k = a;
+            while (k < b) {
+                if (!units[k - a].ok || !units[k - a].out_len) { k++; continue; }
+                size_t e = k;
+                uint64_t bytes = units[k - a].out_len;
+                while (e + 1 < b && units[e + 1 - a].ok && units[e - a].out_len == units[e - a].out_cap && ids[e + 1] == ids[e] + 1 &&
+                       units[e + 1 - a].d_out_off == units[e - a].d_out_off + units[e - a].out_cap) {
+                    e++;
+                    bytes = units[e - a].d_out_off + units[e - a].out_len - units[k - a].d_out_off;
+                }
+                ok = ok && CZ_CUDA(cudaMemcpyAsync(out + out_off[ids[k]], bk->d_out() + units[k - a].d_out_off, bytes, cudaMemcpyDeviceToHost, bk->st));
+                k = e + 1;
             }
             if (!ok || !CZ_CUDA(cudaStreamSynchronize(bk->st))) return CZ_E_MEM;
+            bk->mark("d2h");
             for (size_t k = a; k < b; k++) {
                 const BigUnit &U = units[k - a];
                 if (!U.ok) continue;

@@ -44,37 +44,54 @@ __device__ __forceinline__ uint32_t cand_bits(const uint32_t *words, uint64_t po
     return __funnelshift_r(lo, hi, sh) & ((1u << n) - 1u);
 }
 
-// Full check of a dynamic block header at absolute bit `b` (the cheap filters have passed). Lane-serial, rare.
-__device__ inline bool cand_full_check(const uint32_t *words, uint64_t b, uint64_t end_bit, uint32_t hlit, uint32_t hdist, uint32_t hclen) {
-    uint64_t pos = b + 17;
-    if (pos + 3ull * hclen > end_bit) return false;
-    // code-length code: lengths in the permuted order, canonical codes, 128-entry table: symbol << 3 | length
+// 64 bits at absolute bit position pos (three aligned word loads)
+__device__ __forceinline__ uint64_t cand_bits64(const uint32_t *words, uint64_t pos) {
+    const uint64_t wi = pos >> 5;
+    const uint32_t sh = (uint32_t)(pos & 31);
+    const uint32_t w0 = __ldg(words + wi), w1 = __ldg(words + wi + 1), w2 = __ldg(words + wi + 2);
+    return (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+}
+
+// Kraft weight of three 3-bit code lengths (7-bit code-length code: a length l weighs 128 >> l), for the 512-entry table
+__host__ __device__ inline uint32_t cand_kraft9(uint32_t x) {
+    uint32_t k = 0;
+    for (int f = 0; f < 3; f++) { const uint32_t l = (x >> (3 * f)) & 7; if (l) k += 128u >> l; }
+    return k;
+}
+
+// Full check of a dynamic block header at absolute bit `b`: the cheap filters have passed and the code-length code (its hclen
+// 3-bit lengths are the low bits of `clbits`, in transmission order) is complete. Lane-serial, rare.
+__device__ inline bool cand_full_check(const uint32_t *words, uint64_t b, uint64_t end_bit, uint32_t hlit, uint32_t hdist, uint32_t hclen,
+                                       uint64_t clbits) {
+    uint64_t pos = b + 17 + 3ull * hclen;
     const uint64_t order_lo = 16ull | (17ull << 5) | (18ull << 10) | (0ull << 15) | (8ull << 20) | (7ull << 25) |
                               (9ull << 30) | (6ull << 35) | (10ull << 40) | (5ull << 45) | (11ull << 50) | (4ull << 55);
     const uint64_t order_hi = 12ull | (3ull << 5) | (13ull << 10) | (2ull << 15) | (14ull << 20) | (1ull << 25) | (15ull << 30);
-    uint64_t cl_lens = 0;
+    uint64_t cl_lens = 0;  // 19 x 3 bits, indexed by symbol
     for (uint32_t i = 0; i < hclen; i++) {
-        const uint32_t l = cand_bits(words, pos, 3);
-        pos += 3;
+        const uint32_t l = (uint32_t)(clbits >> (3 * i)) & 7;
         const uint32_t sym = i < 12 ? (uint32_t)(order_lo >> (5 * i)) & 31 : (uint32_t)(order_hi >> (5 * (i - 12))) & 31;
         cl_lens |= (uint64_t)l << (3 * sym);
     }
-    uint32_t cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (uint32_t s = 0; s < 19; s++) cnt[(cl_lens >> (3 * s)) & 7]++;
-    uint32_t next[8], code = 0;
-    int left = 1;
-    for (uint32_t len = 1; len <= 7; len++) {
-        left = (left << 1) - (int)cnt[len];
-        if (left < 0) return false;
-        next[len] = code;
-        code = (code + cnt[len]) << 1;
+    // canonical codes of the (complete) code-length code: symbols per length and first code per length, packed
+    uint64_t cntp = 0;  // 5 bits per length
+    for (uint32_t s = 0; s < 19; s++) {
+        const uint32_t l = (uint32_t)(cl_lens >> (3 * s)) & 7;
+        if (l) cntp += 1ull << (5 * l);
     }
-    if (left != 0) return false;  // zlib: an incomplete code-length code is always an error
-    uint8_t cl_tab[128];
+    uint64_t nextp = 0;  // 8 bits per length
+    uint32_t code = 0;
+    for (uint32_t len = 1; len <= 7; len++) {
+        const uint32_t c = (uint32_t)(cntp >> (5 * len)) & 31;
+        nextp |= (uint64_t)code << (8 * len);
+        code = (code + c) << 1;
+    }
+    uint8_t cl_tab[128];  // symbol << 3 | length (a complete code fills every entry)
     for (uint32_t s = 0; s < 19; s++) {
         const uint32_t l = (uint32_t)(cl_lens >> (3 * s)) & 7;
         if (!l) continue;
-        const uint32_t c = next[l]++;
+        const uint32_t c = (uint32_t)(nextp >> (8 * l)) & 0xff;
+        nextp += 1ull << (8 * l);
         const uint32_t rev = __brev(c) >> (32 - l);
         for (uint32_t idx = rev; idx < 128; idx += (1u << l)) cl_tab[idx] = (uint8_t)((s << 3) | l);
     }
@@ -112,8 +129,14 @@ __device__ inline bool cand_full_check(const uint32_t *words, uint64_t b, uint64
     return true;
 }
 
-// cand[c] = absolute bit of the first plausible dynamic block header in chunk c, or ~0.
+// cand[c] = absolute bit of the first plausible dynamic block header in chunk c, or ~0. Three filters of rising cost per bit
+// offset: the 17 header bits (BFINAL = 0, BTYPE = 10, HLIT / HDIST in range: ~11 % of random offsets pass); the Kraft sum of
+// the code-length code from a table over 9 bits (three lengths) at a time — it must be complete, which ~0.5 % of those are;
+// then the full decode of the code lengths.
 __global__ void __launch_bounds__(128) inflate_candidates_kernel(const uint8_t *in, const CandChunk *chunks, uint32_t n_chunks, uint64_t *cand) {
+    __shared__ uint8_t kraft9[512];
+    for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) kraft9[i] = (uint8_t)cand_kraft9(i);
+    __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (c >= n_chunks) return;
@@ -122,14 +145,22 @@ __global__ void __launch_bounds__(128) inflate_candidates_kernel(const uint8_t *
     uint64_t found = ~0ull;
     for (uint64_t base = ch.lo_bit; base < ch.hi_bit && found == ~0ull; base += 32) {
         const uint64_t b = base + lane;
-        bool ok = b < ch.hi_bit && b + 17 + 12 <= ch.end_bit;
+        bool ok = b < ch.hi_bit && b + 17 + 57 + 14 <= ch.end_bit;
         uint32_t hlit = 0, hdist = 0, hclen = 0;
+        uint64_t clbits = 0;
         if (ok) {
             const uint32_t h = cand_bits(words, b, 17);
             hlit = (h >> 3) & 31; hdist = (h >> 8) & 31; hclen = ((h >> 13) & 15) + 4;
             ok = (h & 7u) == 4u && hlit <= 29 && hdist <= 29;  // BFINAL = 0, BTYPE = 10
         }
-        if (ok) ok = cand_full_check(words, b, ch.end_bit, hlit, hdist, hclen);
+        if (ok) {
+            clbits = cand_bits64(words, b + 17) & ((1ull << (3 * hclen)) - 1ull);  // 3 * hclen <= 57
+            uint32_t k = 0;
+#pragma unroll
+            for (int f = 0; f < 7; f++) k += kraft9[(uint32_t)(clbits >> (9 * f)) & 511u];
+            ok = k == 128u;  // zlib: an incomplete (or over-subscribed) code-length code is always an error
+        }
+        if (ok) ok = cand_full_check(words, b, ch.end_bit, hlit, hdist, hclen, clbits);
         const uint32_t m = __ballot_sync(CZK_FULL, ok);
         if (m) found = base + (uint32_t)(__ffs((int)m) - 1);
     }

@@ -24,7 +24,8 @@ struct BigUnit {
     uint64_t in_len = 0;
     uint64_t d_in_lo = 0;            // byte offset of the stream in the backend's device input buffer
     uint64_t out_cap = 0;            // the caller's slot: a stream that needs more is left to the serial path
-    uint64_t d_out_off = 0;          // OUT: byte offset of its bytes in the backend's device output buffer (ok units)
+    uint64_t d_out_off = 0;          // byte offset of its slot in the backend's device output buffer (slots must not overlap;
+                                     // mirroring the caller's layout lets neighbouring units leave in one copy)
     int window_bits = 15;            // -15 raw, 15 zlib, 31 gzip, 47 auto
     // out
     bool ok = false;
@@ -46,6 +47,7 @@ struct BigUnit {
 //                const uint8_t *d_first, const uint16_t *d_sym, const uint8_t *d_win, uint8_t *d_out, uint32_t *d_bad);
 //   bool check(const uint64_t *d_run_off, const uint64_t *d_final_off, uint32_t n_runs, const uint8_t *d_out, int kind, uint32_t *d_checks);
 //   const czk::CrcTables *crc();
+//   void mark(const char *phase);   // optional timeline hook (CZ_TRACE): called after each phase has been enqueued
 
 static inline uint64_t runs_align(uint64_t v) { return (v + 255) & ~255ull; }
 
@@ -90,6 +92,7 @@ int inflate_runs_batch(BK &bk, std::vector<BigUnit> &units, uint64_t chunk_bytes
         }
     }
     std::vector<uint64_t> cand(chunks.size(), ~0ull);
+    bk.mark("start");
     if (!chunks.empty()) {
         if (!bk.scratch_need(chunks.size() * (sizeof(CandChunk) + 8) + 1024)) return -4;
         CandChunk *d_chunks = (CandChunk *)bk.scratch(sizeof(CandChunk) * chunks.size());
@@ -99,6 +102,7 @@ int inflate_runs_batch(BK &bk, std::vector<BigUnit> &units, uint64_t chunk_bytes
         if (!bk.candidates(d_chunks, (uint32_t)chunks.size(), d_cand)) return -4;
         if (!bk.d2h(cand.data(), d_cand, 8 * chunks.size())) return -4;
     }
+    bk.mark("candidates");
     // ---- 2. runs per unit: start bits relative to the stream's first byte
     struct Run { uint32_t unit; uint64_t start, target; uint32_t mid; uint64_t end, out_len; int32_t status; uint32_t fin; bool counted; };
     std::vector<std::vector<Run>> ur(nu);
@@ -198,6 +202,7 @@ int inflate_runs_batch(BK &bk, std::vector<BigUnit> &units, uint64_t chunk_bytes
             R.swap(keep);
         }
     }
+    bk.mark("count rounds");
     // ---- 4. layout of the units whose chain closed
     struct LRun { uint32_t unit; uint64_t start, target; uint32_t mid; uint64_t out_len; uint32_t first; };
     std::vector<LRun> L;
@@ -232,7 +237,7 @@ int inflate_runs_batch(BK &bk, std::vector<BigUnit> &units, uint64_t chunk_bytes
         uint64_t within = 0, out_total = 0;
         for (size_t i = 0; i < n; i++) {
             BigUnit &U = units[L[i].unit];
-            if (L[i].first) { within = 0; U.d_out_off = out_total; out_total = runs_align(out_total + U.out_len + 16); }
+            if (L[i].first) { within = 0; if (U.d_out_off + U.out_len > out_total) out_total = U.d_out_off + U.out_len; }
             run_off[i + 1] = run_off[i] + L[i].out_len;
             final_off[i] = U.d_out_off + within;
             within += L[i].out_len;
@@ -293,17 +298,28 @@ int inflate_runs_batch(BK &bk, std::vector<BigUnit> &units, uint64_t chunk_bytes
         }
     }
     Q.base.ids = nullptr; Q.base.n = (uint32_t)n;
+    bk.mark("emit");
     if (!bk.zero(d_cnt, 256)) return -4;
     if (!bk.lz16(Q, d_sym)) return -4;
+    bk.mark("lz16");
     if (!bk.window(d_streams, (uint32_t)streams.size(), d_run_off, d_sym, d_win, d_bad)) return -4;
+    bk.mark("window");
     if (!bk.resolve(d_slices, (uint32_t)slices.size(), d_run_off, d_final_off, d_first, d_sym, d_win, bk.d_out(), d_bad)) return -4;
-    if (!bk.check(d_run_off, d_final_off, (uint32_t)n, bk.d_out(), 3, d_checks)) return -4;
+    bk.mark("resolve");
+    int check_kind = 0;  // Adler-32 for zlib containers, CRC-32 for gzip (raw streams need neither)
+    for (size_t si = 0; si < streams.size(); si++) {
+        const BigUnit &U = units[stream_unit[si]];
+        check_kind |= U.window_bits == 15 ? 1 : U.window_bits == 31 ? 2 : U.window_bits == 47 ? 3 : 0;
+    }
+    if (check_kind && !bk.check(d_run_off, d_final_off, (uint32_t)n, bk.d_out(), check_kind, d_checks)) return -4;
+    if (!check_kind && !bk.zero(d_checks, 8 * n)) return -4;
     std::vector<uint32_t> checks(2 * n);
     std::vector<TokMeta> hm(n);
     std::vector<RunResult> hres(n);
     uint32_t bad = 0;
     if (!bk.d2h(checks.data(), d_checks, 8 * n) || !bk.d2h(hm.data(), d_meta, sizeof(TokMeta) * n) ||
         !bk.d2h(hres.data(), d_res, sizeof(RunResult) * n) || !bk.d2h(&bad, d_bad, 4)) return -4;
+    bk.mark("checks");
     // ---- 6. per stream: the emit pass must have reproduced the count pass; fold the checks; container trailer
     for (size_t si = 0; si < streams.size(); si++) {
         BigUnit &U = units[stream_unit[si]];

@@ -114,6 +114,7 @@ struct SimRunsBackend {
     bool d2h(void *h, const void *d, size_t n) { memcpy(h, d, n); return true; }
     bool zero(void *d, size_t n) { memset(d, 0, n); return true; }
     const CrcTables *crc() { return &crc_tab; }
+    void mark(const char *) {}
     bool candidates(const CandChunk *c, uint32_t n, uint64_t *cand) {
         cusim::set_seed(seed++);
         cusim::launch((n + 3) / 4, 128, 0, inflate_candidates_kernel, (const uint8_t *)in, c, n, cand);
@@ -161,6 +162,7 @@ extern "C" int sim_inflate_runs(size_t n, uint8_t *in, const uint64_t *in_off, u
     for (size_t i = 0; i < n; i++) {
         units[i].h_in = in + in_off[i]; units[i].in_len = in_off[i + 1] - in_off[i]; units[i].d_in_lo = in_off[i];
         units[i].out_cap = out_off[i + 1] - out_off[i]; units[i].window_bits = window_bits;
+        units[i].d_out_off = out_off[i] - out_off[0] + 32 * i;  // the caller's layout (plus a guard gap the emulator can check)
     }
     int rc = czh::inflate_runs_batch(bk, units, chunk_bytes);
     for (size_t i = 0; i < n; i++) {
