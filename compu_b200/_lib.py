@@ -41,6 +41,7 @@ SIGNATURES = {
     "cz_deflate_batch": (ci, [sz, vp, vp, vp, vp, vp, vp, ci, ci, ci, u64, u32]),
     "cz_deflate_segmented": (ci, [vp, u64, vp, u64, vp, ci, ci, ci, u64, u32, vp, u64, vp]),
     "cz_inflate_segmented": (ci, [vp, u64, vp, u64, vp, ci, u64, vp, u64, u32]),
+    "cz_has_experiments": (ci, []),
     "cz_tune_inflate": (ci, [ci, ci]),
     "cz_tune_inflate_lz": (ci, [ci, ci]),
     "cz_inflate_workspace_bytes": (u64, [sz, u64]),

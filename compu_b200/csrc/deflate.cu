@@ -45,9 +45,13 @@ struct WsLayout {
 // GiB against 110.4 ms for the single-link walk: the speculative loads of the second candidate cost more than the round trip
 // they save). Off by default; the array is only carved out of the workspace when it is on.
 static bool match_two_links() {
+#ifdef CZ_EXPERIMENTS
     static int v = -1;
     if (v < 0) { const char *e = getenv("CZ_MATCH_LINKS"); v = e ? atoi(e) == 2 : 0; }
     return v != 0;
+#else
+    return false;
+#endif
 }
 
 static WsLayout ws_layout(uint64_t nseg, uint64_t n_units, uint64_t in_bytes) {
@@ -159,8 +163,6 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
     // kernels (its 128-thread CTAs fit beside the match search's one 1 024-thread CTA per SM) and is joined before K5c.
     SideStream *side = P.check_kind ? side_stream_for(st) : nullptr;
     unsigned split_at = 0;  // != 0: segments [split_at, nseg) get their chains on the side stream
-    static const int match_v = [] { const char *e = getenv("CZ_MATCH_V"); return e ? atoi(e) : 3; }();
-    static const bool match_tiled = getenv("CZ_MATCH_TILED") != nullptr, chain_split = getenv("CZ_CHAIN_SPLIT") != nullptr;
     if (P.check_kind) {
         if (side && CZ_CUDA(cudaEventRecord(side->fork, st)) && CZ_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0))) {
             CZ_KL(czk::deflate_checksum_kernel<<<nseg < 65535u * 8u ? nseg : 65535u * 8u, 128, 0, side->stream>>>(P));
@@ -170,6 +172,35 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
             CZ_KL(czk::deflate_checksum_kernel<<<nseg < 65535u * 8u ? nseg : 65535u * 8u, 128, 0, st>>>(P));
         }
     }
+    const bool search = !(P.tune.level0 || P.tune.huffman_only || P.tune.rle_only);
+#ifndef CZ_EXPERIMENTS
+    // K1 chains (warp per segment), then K2 match search: persistent CTAs of 1 024 threads sweep contiguous chunks, so the
+    // 96 KiB neighbourhood of the sweep (32 KiB of input, 64 KiB of links) stays in the SM's L1. Level 0 / HuffmanOnly / Rle
+    // need no chains: the thread-per-position kernel writes their (empty / distance-1) matches.
+    (void)split_at;
+    P.prevd2 = nullptr;
+    if (search) {
+        static const int chain_per_sm = [] { const char *e = getenv("CZ_CHAIN_PER_SM"); return e ? atoi(e) : 12; }();
+        const unsigned cgrid = nseg < (unsigned)ctx->sm_count * (unsigned)chain_per_sm ? nseg : (unsigned)ctx->sm_count * (unsigned)chain_per_sm;
+        CZ_KL(czk::deflate_chain_kernel<<<cgrid, 32, 0, st>>>(P, 0u, nseg));
+        if (prof) cudaEventRecord(pr.m0, st);
+        const unsigned sms = (unsigned)ctx->sm_count;
+        static const long chunk_kb = [] { const char *e = getenv("CZ_MATCH_CHUNK_KB"); return e ? atol(e) : 0l; }();
+        uint64_t chunk = chunk_kb > 0 ? (uint64_t)chunk_kb << 10 : L.in_bytes / ((uint64_t)sms * 8);  // at least ~8 chunks per CTA
+        chunk = (chunk + 65535) & ~65535ull;
+        if (chunk < 65536) chunk = 65536;
+        if (chunk > (1u << 20) && chunk_kb <= 0) chunk = 1u << 20;
+        CZ_KL(czk::deflate_match_sweep_kernel<1024, 1, 0><<<sms, 1024, 0, st>>>(P, L.in_bytes, (uint32_t)chunk, 0u, 0u));
+    } else {
+        if (prof) cudaEventRecord(pr.m0, st);
+        CZ_KL(czk::deflate_match_kernel<<<(unsigned)((L.in_bytes + 255) / 256 ? (L.in_bytes + 255) / 256 : 1), 256, 0, st>>>(P, L.in_bytes));
+    }
+#else
+    // experiments build: every chain / match-search variant stays selectable (CZ_MATCH_V, CZ_MATCH_TILED, CZ_MATCH_LINKS,
+    // CZ_CHAIN_SPLIT); measurements in profiles/r1_notes.md
+    static const int match_v = [] { const char *e = getenv("CZ_MATCH_V"); return e ? atoi(e) : 3; }();
+    static const bool match_tiled = getenv("CZ_MATCH_TILED") != nullptr, chain_split = getenv("CZ_CHAIN_SPLIT") != nullptr;
+    (void)search;
     if (!P.tune.level0 && !P.tune.huffman_only && !P.tune.rle_only) {
         static int chain_per_sm = -1;
         if (chain_per_sm < 0) { const char *e = getenv("CZ_CHAIN_PER_SM"); chain_per_sm = e ? atoi(e) : 12; }
@@ -237,6 +268,7 @@ static int launch_deflate(cudaStream_t st, DeviceCtx *ctx, const DeflateLaunch &
         const unsigned tiles = (unsigned)((L.in_bytes >> 12) + L.nseg + 1);
         CZ_KL(czk::deflate_match_tiled_kernel<<<tiles, CZK_MT_THREADS, smem, st>>>(P));
     }
+#endif  // CZ_EXPERIMENTS
     {
     if (prof) cudaEventRecord(pr.m1, st);
         // one wave of 64-position sub-tiles when the segments fit 16 warps per SM, else 32-position sub-tiles at 28 per SM

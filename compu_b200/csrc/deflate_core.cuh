@@ -230,7 +230,7 @@ __host__ __device__ inline uint32_t find_match(const uint8_t *seg, uint32_t seg_
     return best_len | (best_dist << 9);
 }
 
-#if defined(__CUDACC__) || defined(CUSIM)
+#if (defined(__CUDACC__) || defined(CUSIM)) && defined(CZ_EXPERIMENTS)
 // find_match() for 32 positions at once, called by all lanes of a warp (lanes without a position pass valid = false).
 // Same candidates in the same order with the same rules per lane, but the warp alternates between two phases instead of
 // letting every lane run its own loop: WALK — lanes follow their chains until each has found a candidate that passes the

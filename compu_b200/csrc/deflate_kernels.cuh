@@ -212,6 +212,7 @@ __global__ void __launch_bounds__(32) deflate_chain_kernel(DeflateParams P, uint
     }
 }
 
+#ifdef CZ_EXPERIMENTS
 // ------------------------------------------------------------------ K1b
 // Second link of every chain node: prevd2[i] = prevd[i] + prevd[i - prevd[i]] (0 = none, or farther than the window).
 // With it the match search fetches two candidates per memory round trip (find_match).
@@ -242,6 +243,8 @@ __global__ void __launch_bounds__(256) deflate_chain2_kernel(DeflateParams P, ui
     }
     P.prevd2[g] = (uint16_t)d2;
 }
+
+#endif  // CZ_EXPERIMENTS
 
 // ------------------------------------------------------------------ K2
 // 256 consecutive input bytes per CTA; a tile may straddle segment boundaries.
@@ -357,14 +360,18 @@ __global__ void __launch_bounds__(THREADS, MINB) deflate_match_sweep_kernel(Defl
                 const uint64_t base = seg_base(P, seg);
                 const uint32_t pos = valid ? (uint32_t)(g - base) : 0u;
                 uint32_t r;
+#ifdef CZ_EXPERIMENTS
                 if (MODE == 1) r = find_match_warp(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, valid);
-                else r = valid ? find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, LINKS2 ? P.prevd2 + base : nullptr) : 0u;
+                else
+#endif
+                r = valid ? find_match(P.in + P.seg_off[seg], seg_len(P, seg), P.prevd + base, pos, P.tune, LINKS2 ? P.prevd2 + base : nullptr) : 0u;
                 if (valid) P.match[g] = r;
             }
         }
     }
 }
 
+#ifdef CZ_EXPERIMENTS
 // ------------------------------------------------------------------ K2 (candidate pairs; experiment, CZ_MATCH_V=2)
 // (Measured on B200: 92 ms per GiB against 77 ms for the simple kernel — every candidate is extended, while find_match()
 // skips the ones that cannot beat the best so far — so it is off by default.)
@@ -633,6 +640,8 @@ __global__ void __launch_bounds__(CZK_MT_THREADS) deflate_match_tiled_kernel(Def
         }
     }
 }
+
+#endif  // CZ_EXPERIMENTS
 
 // ------------------------------------------------------------------ K3
 // One warp per segment. The parse is a serial chain (the next position depends on the match taken at this one). The warp

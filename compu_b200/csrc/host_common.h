@@ -90,10 +90,6 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
                    uint32_t *d_checks, int window_bits, int segment_mode, int check_kind, void *d_ws, uint64_t ws_bytes,
                    uint64_t total_out_bytes, const uint32_t *d_ids, size_t n_ids, int big);
 uint64_t inflate_workspace_bytes(size_t n, uint64_t total_out_bytes);
-int launch_inflate_count(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
-                         const uint64_t *d_out_off, uint64_t *d_out_lens, int32_t *d_statuses, uint64_t *d_in_consumed,
-                         int window_bits, int segment_mode, void *d_ws, uint64_t ws_bytes);
-
 }  // namespace czh
 namespace czk { struct ResumeState; }
 namespace czh {

@@ -6,8 +6,14 @@
 #include <chrono>
 
 #include "host_common.h"
+// The default build holds the kernels the product runs: inflate_tok_kernel + inflate_lz_kernel (two-phase path),
+// inflate_kernel<1, 8> (warp per stream: big units the block-parallel path declines, the resumable streaming decoder) and the
+// run kernels of inflate_runs.cuh. The variants that measured slower (profiles/r1_notes.md) are only compiled with
+// -DCZ_EXPERIMENTS (make EXPERIMENTS=1); cz_has_experiments() says which build is loaded.
 #include "inflate_kernel.cuh"
+#ifdef CZ_EXPERIMENTS
 #include "inflate_lane_kernel.cuh"
+#endif
 #include "inflate_lc_kernel.cuh"
 #include "inflate_two_phase.cuh"
 #include "inflate_runs_host.h"
@@ -40,6 +46,7 @@ static int launch_cfg(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams 
     return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
 }
 
+#ifdef CZ_EXPERIMENTS
 // "one lane = one stream" variant: LB/DB = log2 of the primary litlen / distance table sizes, W warps per CTA (1 CTA per SM)
 template <int LB, int DB, int W>
 static int launch_lane(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams &P) {
@@ -82,6 +89,8 @@ static int launch_lc(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams &
     return CZ_CUDA(cudaGetLastError()) ? 0 : CZ_E_MEM;
 }
 
+#endif  // CZ_EXPERIMENTS
+
 // Two-phase path (default): phase A = lane-per-stream Huffman decode into tokens, phase B = warp-per-stream LZ77 resolution.
 // Workspace: [counter A 128 B | counter B 128 B] [TokMeta n] [token words total_out + 8 n]
 static inline uint64_t two_phase_meta_off() { return 256; }
@@ -115,6 +124,7 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
     Q.meta = (czk::TokMeta *)((uint8_t *)d_ws + two_phase_meta_off());
     Q.tok = (uint32_t *)((uint8_t *)d_ws + two_phase_tok_off(n_span));
     Q.counter_c = (unsigned long long *)((uint8_t *)d_ws + 192);
+#ifdef CZ_EXPERIMENTS
     // phase B of units whose output slot fits the shared-memory tile runs one CTA per unit (CZ_LZ_CTA=0: off)
     if (g_lz_cta < 0) { const char *e = getenv("CZ_LZ_CTA"); g_lz_cta = e ? atoi(e) : 0; }
     if (g_lz_spin < 0) { const char *e = getenv("CZ_LZ_SPIN_NS"); g_lz_spin = e ? atoi(e) : 100; }
@@ -124,17 +134,23 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
     auto kc = czk::inflate_lz_cta_kernel<WC, 32 / WC>;
     auto kc4 = czk::inflate_lz_cta_kernel<4, 8>;
     const size_t smem_c = czk::inflate_lz_cta_smem_bytes<WC>();
+#endif
     auto ka = czk::inflate_tok_kernel<WA>;
     auto kb = czk::inflate_lz_kernel<WB, H>;
     const size_t smem = czk::inflate_tok_smem_bytes<WA>();
     static bool configured[64] = {};
-    static int per_sm_a[64], per_sm_b[64], per_sm_c[64];
+    static int per_sm_a[64], per_sm_b[64];
     const int d = ctx->dev & 63;
+#ifdef CZ_EXPERIMENTS
+    static int per_sm_c[64];
+#endif
     if (!configured[d]) {
+#ifdef CZ_EXPERIMENTS
         if (!CZ_CUDA(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c))) return CZ_E_MEM;
         if (!CZ_CUDA(cudaFuncSetAttribute(kc4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c))) return CZ_E_MEM;
         if (!CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c[d], kc, WC * 32, smem_c))) return CZ_E_MEM;
         if (per_sm_c[d] < 1) { set_error("inflate_lz_cta_kernel does not fit on an SM"); return CZ_E_MEM; }
+#endif
         if (!CZ_CUDA(cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return CZ_E_MEM;
         if (!CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a[d], ka, WA * 32, smem))) return CZ_E_MEM;
         if (!CZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b[d], kb, WB * 32, 0))) return CZ_E_MEM;
@@ -164,17 +180,20 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
     } else
     CZ_KL(ka<<<(unsigned)ga, WA * 32, smem, st>>>(Q));
     if (g_prof_on) cudaEventRecord(pr.e1, st);
+#ifdef CZ_EXPERIMENTS
     if (Q.cta_tile) {
         uint64_t gc = P.n, gcmax = (uint64_t)ctx->sm_count * per_sm_c[d];
         if (gc > gcmax) gc = gcmax;
         if (g_lz_cta == 2) CZ_KL(kc4<<<(unsigned)gc, 4 * 32, smem_c, st>>>(Q));
         else CZ_KL(kc<<<(unsigned)gc, WC * 32, smem_c, st>>>(Q));
     }
+#endif
     uint64_t gb = (P.n + WB - 1) / WB;
     static int lz_cap = -1;  // experiment knob: CTAs of phase B per SM (fewer streams in flight => their windows fit L2)
     if (lz_cap < 0) { const char *e = getenv("CZ_LZ_CTAS_PER_SM"); lz_cap = e ? atoi(e) : 0; }
     gmax = (uint64_t)ctx->sm_count * (lz_cap > 0 && lz_cap < per_sm_b[d] ? lz_cap : per_sm_b[d]);
     if (gb > gmax) gb = gmax;
+#ifdef CZ_EXPERIMENTS
     // phase B variants with several tokens per lane (cz_tune_inflate_lz / CZ_LZ_CTA = 3..7)
 #define CZ_LZW(mode, TPL, SHORT, MINB)                                                                              \
     if (g_lz_cta == mode) {                                                                                         \
@@ -187,6 +206,7 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
     } else
     CZ_LZW(3, 2, 12, 3) CZ_LZW(4, 2, 12, 2) CZ_LZW(5, 4, 8, 2) CZ_LZW(6, 2, 8, 4) CZ_LZW(7, 4, 8, 3)
 #undef CZ_LZW
+#endif
     CZ_KL(kb<<<(unsigned)gb, WB * 32, 0, st>>>(Q));
     if (g_prof_on) {
         cudaEventRecord(pr.e2, st);
@@ -200,24 +220,6 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
 static int par_decode_off() {
     static const int v = getenv("CZ_PAR_DECODE") ? 0 : 1;
     return v;
-}
-
-// Counting mode: output size, status and consumed bytes of every unit, no output bytes (the speculative split's verify pass).
-// Runs the warp-per-stream kernel (a lone decoder lane per unit is ~6x faster per stream than the lane-per-stream kernels,
-// and pieces are few and large). Workspace: 256 B.
-int launch_inflate_count(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_in, const uint64_t *d_in_off,
-                         const uint64_t *d_out_off, uint64_t *d_out_lens, int32_t *d_statuses, uint64_t *d_in_consumed,
-                         int window_bits, int segment_mode, void *d_ws, uint64_t ws_bytes) {
-    if (n == 0) return 0;
-    if (n > 0xfffffff0u || !d_ws || ws_bytes < 256) { set_error("inflate count workspace too small"); return CZ_E_MEM; }
-    czk::InflateParams P;
-    memset(&P, 0, sizeof P);
-    P.in = d_in; P.in_off = d_in_off; P.out = nullptr; P.out_off = d_out_off; P.out_lens = d_out_lens; P.statuses = d_statuses;
-    P.in_consumed = d_in_consumed; P.checks = nullptr; P.counter = (unsigned long long *)d_ws; P.crc = ctx->d_crc;
-    P.n = (uint32_t)n; P.ids = nullptr; P.window_bits = window_bits; P.segment_mode = segment_mode; P.check_kind = 0;
-    P.count_only = 1; P.serial_only = par_decode_off();
-    if (!CZ_CUDA(cudaMemsetAsync(d_ws, 0, 256, st))) return CZ_E_MEM;
-    return launch_cfg<1, 8>(st, ctx, P);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -298,6 +300,10 @@ struct CudaRunsBackend {
         uint64_t g = (Q.base.n + 7) / 8, gmax = (uint64_t)ctx->sm_count * per_sm_lz16;
         if (g > gmax) g = gmax;
         CZ_KL(czk::inflate_lz16_kernel<8><<<(unsigned)g, 256, 0, st>>>(Q, sym));
+        return ok();
+    }
+    bool tail_markers(const uint64_t *run_off, uint32_t n, const uint16_t *sym, uint8_t *flags) {
+        CZ_KL(czk::inflate_tail_markers_kernel<8><<<(n + 7) / 8, 256, 0, st>>>(run_off, n, sym, flags));
         return ok();
     }
     bool window(const czk::RunStream *s, uint32_t ns, const uint64_t *run_off, const uint16_t *sym, uint8_t *win, uint32_t *bad) {
@@ -451,12 +457,15 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
     // big units (one stream is megabytes): one WARP per stream, a single decoder lane feeding warp-cooperative LZ77 rounds —
     // about 6x the single-stream speed of the lane-per-stream kernels, which only pay off across thousands of streams
     if (big) return launch_cfg<1, 8>(st, ctx, P);
+    // default configurations
+    if (c.D == 1 && c.W == 8) return launch_cfg<1, 8>(st, ctx, P);
+    if (c.D == -2 && (c.W == 14 || c.W == 0)) return launch_two_phase<14, 8, 0>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+#ifdef CZ_EXPERIMENTS
 #define CZ_CFG(d, w) if (c.D == d && c.W == w) return launch_cfg<d, w>(st, ctx, P)
-    CZ_CFG(1, 8); CZ_CFG(2, 8); CZ_CFG(4, 7); CZ_CFG(4, 4); CZ_CFG(8, 7); CZ_CFG(8, 4); CZ_CFG(8, 2); CZ_CFG(16, 3);
+    CZ_CFG(2, 8); CZ_CFG(4, 7); CZ_CFG(4, 4); CZ_CFG(8, 7); CZ_CFG(8, 4); CZ_CFG(8, 2); CZ_CFG(16, 3);
     CZ_CFG(16, 1); CZ_CFG(32, 1);
 #undef CZ_CFG
     // D = -2: two-phase, W = rounds per iteration of phase B (loads in flight per lane)
-    if (c.D == -2 && (c.W == 14 || c.W == 0)) return launch_two_phase<14, 8, 0>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
     if (c.D == -2 && c.W == 2) return launch_two_phase<14, 8, 2>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
     if (c.D == -2 && c.W == -8) return launch_two_phase<14, 8, -8>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
     if (c.D == -2 && c.W == -12) return launch_two_phase<14, 8, -12>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
@@ -483,7 +492,8 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
     if (c.D == -8 && c.W == 7) return launch_lane<8, 7, 4>(st, ctx, P);
     if (c.D == -10 && c.W == 8) return launch_lane<10, 8, 2>(st, ctx, P);
     if (c.D == -9 && c.W == 7) return launch_lane<9, 7, 3>(st, ctx, P);
-    set_error("CZ_INFLATE_CFG=%d,%d is not an instantiated configuration", c.D, c.W);
+#endif
+    set_error("inflate configuration %d,%d is not in this build (experiments need make EXPERIMENTS=1)", c.D, c.W);
     return CZ_E_STREAM;
 }
 
@@ -491,7 +501,18 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
 
 using namespace czh;
 
+extern "C" int cz_has_experiments(void) {
+#ifdef CZ_EXPERIMENTS
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 extern "C" int cz_tune_inflate_lz(int cta_mode, int spin_ns) {
+#ifndef CZ_EXPERIMENTS
+    if (cta_mode != 0) { set_error("phase B variants need a build with -DCZ_EXPERIMENTS"); return CZ_E_STREAM; }
+#endif
     g_lz_cta = cta_mode;
     g_lz_spin = spin_ns;
     return 0;
@@ -500,6 +521,12 @@ extern "C" int cz_tune_inflate_lz(int cta_mode, int spin_ns) {
 extern "C" uint64_t cz_inflate_workspace_bytes(size_t n, uint64_t total_out_bytes) { return inflate_workspace_bytes(n, total_out_bytes); }
 
 extern "C" int cz_tune_inflate(int slots_per_warp, int warps_per_cta) {
+#ifndef CZ_EXPERIMENTS
+    if (!((slots_per_warp == -2 && (warps_per_cta == 14 || warps_per_cta == 0)) || (slots_per_warp == 1 && warps_per_cta == 8))) {
+        set_error("inflate configuration %d,%d needs a build with -DCZ_EXPERIMENTS", slots_per_warp, warps_per_cta);
+        return CZ_E_STREAM;
+    }
+#endif
     g_cfg.D = slots_per_warp;
     g_cfg.W = warps_per_cta;
     return 0;

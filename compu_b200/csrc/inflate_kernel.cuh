@@ -633,6 +633,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
         // by the ~5-cycle dependent issue distance, and a round (two look-ups for 64 offsets, ~5 shuffle hops of the chase,
         // compaction) is ~35 dependent instructions per token against ~50 for the serial lane. OFF by default (CZ_PAR_DECODE=1).
         bool par_eob = false;
+#ifdef CZ_EXPERIMENTS
         if constexpr (D == 1) {
             const bool can = !P.serial_only && !resumable && __shfl_sync(CZK_FULL, (int)(st == SS_DECODE), 0) != 0;
             if (can) {
@@ -713,6 +714,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_kernel(InflateParams P) {
             }
         }
 
+#endif  // CZ_EXPERIMENTS
         // ---- (5) Huffman decode: D lanes, each its own stream, up to CZK_TOKENS tokens
         if (st == SS_DECODE && !par_eob) {
             uint32_t *tok = my.u.tokens;

@@ -228,6 +228,9 @@ __device__ inline int lc_parse_dynamic(BitReader &br, LcSlot &sm, uint32_t &nlit
 
 #define CZK_LC_BUDGET 256  // symbols decoded per lane between two visits of the block-level phases
 
+#ifdef CZ_EXPERIMENTS  // the single-kernel lane-per-stream design (77 GB/s on cfg2: 65 536 windows thrash L2); the default path
+                       // only uses the slot layout, the table construction and the canonical decode above
+
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) inflate_lc_kernel(InflateParams P) {
     CZ_DYNAMIC_SMEM(smem_raw);
@@ -540,5 +543,6 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_lc_kernel(InflateParams P)
 
 template <int WARPS>
 constexpr size_t inflate_lc_smem_bytes() { return 1152 + WARPS * 256 + sizeof(LcSlot) * 32 * (size_t)WARPS; }
+#endif  // CZ_EXPERIMENTS
 
 }  // namespace czk

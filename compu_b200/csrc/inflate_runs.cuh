@@ -293,9 +293,37 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_L
 // 4. windows: per stream, serially over its runs. win[r] (32 KiB) = the 32 KiB of final bytes that precede run r + 1, i.e.
 // the last 32 KiB up to the end of run r (zero-filled where the stream is shorter; such positions are never referenced by a
 // valid stream — a marker that points there is reported through `bad`).
+// The chain is cut wherever it can be: a run of at least 32 KiB whose last 32 KiB hold no marker has a window that does not
+// depend on anything before it (streams with full-flush points — ours, pigz's — break every segment), so the kernel works on
+// CHAINS: runs [first_run, first_run + n_runs) of one stream, the first of which starts the stream or is such a breaker.
 struct RunStream {
-    uint32_t first_run, n_runs;  // runs [first_run, first_run + n_runs) of the launch belong to this stream, in order
+    uint32_t first_run, n_runs;
+    uint64_t stream_start;       // offset (symbol space) of the first byte of the stream the chain belongs to
 };
+
+// flags[r] = 0 when run r is a chain breaker (>= 32 KiB long, no marker in its last 32 KiB), else 1. One warp per run.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) inflate_tail_markers_kernel(const uint64_t *run_off, uint32_t n_runs, const uint16_t *sym, uint8_t *flags) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (r >= n_runs) return;
+    const uint64_t a = run_off[r], e = run_off[r + 1];
+    uint32_t any = e - a < 32768 ? 1u : 0u;
+    if (!any) {
+        // 16-byte loads where the tail is aligned (symbol offsets are even byte addresses; the head up to alignment goes singly)
+        uint64_t p = e - 32768;
+        while ((p & 7) && p < e) { if (lane == 0) any |= sym[p] >> 15; p++; }
+        const uint4 *v = (const uint4 *)(sym + p);
+        const uint64_t nv = (e - p) >> 3;
+        for (uint64_t k = lane; k < nv; k += 32) {
+            const uint4 x = v[k];
+            any |= ((x.x | x.y | x.z | x.w) & 0x80008000u) ? 1u : 0u;
+        }
+        for (uint64_t q = p + nv * 8 + lane; q < e; q += 32) any |= sym[q] >> 15;
+    }
+    any = __any_sync(CZK_FULL, any != 0);
+    if (lane == 0) flags[r] = (uint8_t)any;
+}
 
 // run_off[n_runs + 1]: the runs' offsets in the launch's compact symbol space (run r = sym[run_off[r], run_off[r + 1])).
 #define CZK_WINDOW_SMEM 65536
@@ -305,7 +333,7 @@ __global__ void __launch_bounds__(1024) inflate_window_kernel(const RunStream *s
     uint8_t (*W)[32768] = (uint8_t (*)[32768])smem_raw;
     const RunStream rs = streams[blockIdx.x];
     const uint32_t tid = threadIdx.x;
-    const uint64_t stream_start = run_off[rs.first_run];
+    const uint64_t stream_start = rs.stream_start;
     int cur = 0;
     uint32_t my_bad = 0;
     for (uint32_t k = 0; k < rs.n_runs; k++) {

@@ -42,6 +42,7 @@ struct BigUnit {
 //   bool h2d(void *d, const void *h, size_t n); bool d2h(void *h, const void *d, size_t n); bool zero(void *d, size_t n);
 //   bool candidates(const czk::CandChunk *d_chunks, uint32_t n, uint64_t *d_cand);
 //   bool tok(const czk::TwoPhaseParams &Q); bool lz16(const czk::TwoPhaseParams &Q, uint16_t *d_sym);
+//   bool tail_markers(const uint64_t *d_run_off, uint32_t n_runs, const uint16_t *d_sym, uint8_t *d_flags);
 //   bool window(const czk::RunStream *d_streams, uint32_t n_streams, const uint64_t *d_run_off, const uint16_t *d_sym, uint8_t *d_win, uint32_t *d_bad);
 //   bool resolve(const czk::RunSlice *d_slices, uint32_t n_slices, const uint64_t *d_run_off, const uint64_t *d_final_off,
 //                const uint8_t *d_first, const uint16_t *d_sym, const uint8_t *d_win, uint8_t *d_out, uint32_t *d_bad);
@@ -219,7 +220,7 @@ int inflate_runs_batch(BK &bk, std::vector<BigUnit> &units, uint64_t chunk_bytes
         }
         if (!closed || total > units[u].out_cap) continue;  // (too small a slot: the serial path reports NeedOutput exactly)
         RunStream s;
-        s.first_run = (uint32_t)L.size(); s.n_runs = (uint32_t)R.size();
+        s.first_run = (uint32_t)L.size(); s.n_runs = (uint32_t)R.size(); s.stream_start = 0;
         for (size_t r = 0; r < R.size(); r++)
             L.push_back(LRun{(uint32_t)u, R[r].start, r + 1 < R.size() ? R[r + 1].start : ~0ull, R[r].mid, R[r].out_len, r == 0 ? 1u : 0u});
         streams.push_back(s);
@@ -250,8 +251,7 @@ int inflate_runs_batch(BK &bk, std::vector<BigUnit> &units, uint64_t chunk_bytes
     }
     const uint64_t total_sym = run_off[n];
     bk.scratch_reset();
-    if (!bk.scratch_need(n * (sizeof(RunDesc) + sizeof(RunResult) + sizeof(TokMeta) + 8 + 8 + 1 + 8 + 4 + 4 + 8 + 32768) +
-                         sizeof(RunStream) * streams.size() + sizeof(RunSlice) * (slices.size() + 1) + 4 * (total_sym + 8 * n) + 2 * total_sym +
+    if (!bk.scratch_need(n * (sizeof(RunDesc) + sizeof(RunResult) + sizeof(TokMeta) + 8 + 8 + 1 + 8 + 4 + 4 + 8 + 32768 + sizeof(RunStream) + 1) + sizeof(RunSlice) * (slices.size() + 1) + 4 * (total_sym + 8 * n) + 2 * total_sym +
                          24 * 256 + 4096)) return -4;
     RunDesc *d_runs = (RunDesc *)bk.scratch(sizeof(RunDesc) * n);
     RunResult *d_res = (RunResult *)bk.scratch(sizeof(RunResult) * n);
@@ -265,16 +265,16 @@ int inflate_runs_batch(BK &bk, std::vector<BigUnit> &units, uint64_t chunk_bytes
     uint32_t *d_checks = (uint32_t *)bk.scratch(8 * n);
     unsigned long long *d_cnt = (unsigned long long *)bk.scratch(256);
     uint32_t *d_bad = (uint32_t *)bk.scratch(256);
-    RunStream *d_streams = (RunStream *)bk.scratch(sizeof(RunStream) * streams.size());
+    RunStream *d_streams = (RunStream *)bk.scratch(sizeof(RunStream) * n);  // chains: at most one per run
+    uint8_t *d_flags = (uint8_t *)bk.scratch(n);
     RunSlice *d_slices = (RunSlice *)bk.scratch(sizeof(RunSlice) * (slices.size() + 1));
     uint32_t *d_tok = (uint32_t *)bk.scratch(4 * (total_sym + 8 * n) + 256);
     uint16_t *d_sym = (uint16_t *)bk.scratch(2 * total_sym + 256);
     uint8_t *d_win = (uint8_t *)bk.scratch(32768ull * n);
     if (!d_runs || !d_res || !d_meta || !d_run_off || !d_final_off || !d_first || !d_lens || !d_stat || !d_ids || !d_checks || !d_cnt ||
-        !d_bad || !d_streams || !d_slices || !d_tok || !d_sym || !d_win) return -4;
+        !d_bad || !d_streams || !d_flags || !d_slices || !d_tok || !d_sym || !d_win) return -4;
     if (!bk.h2d(d_runs, hr.data(), sizeof(RunDesc) * n) || !bk.h2d(d_run_off, run_off.data(), 8 * (n + 1)) ||
         !bk.h2d(d_final_off, final_off.data(), 8 * n) || !bk.h2d(d_first, is_first.data(), n) ||
-        !bk.h2d(d_streams, streams.data(), sizeof(RunStream) * streams.size()) ||
         !bk.h2d(d_slices, slices.data(), sizeof(RunSlice) * slices.size()) || !bk.zero(d_bad, 256)) return -4;
     // ---- 5. emit tokens (per container kind, as in the count pass), resolve into symbols, windows, bytes, checks
     TwoPhaseParams Q;
@@ -302,7 +302,21 @@ int inflate_runs_batch(BK &bk, std::vector<BigUnit> &units, uint64_t chunk_bytes
     if (!bk.zero(d_cnt, 256)) return -4;
     if (!bk.lz16(Q, d_sym)) return -4;
     bk.mark("lz16");
-    if (!bk.window(d_streams, (uint32_t)streams.size(), d_run_off, d_sym, d_win, d_bad)) return -4;
+    // chains for the window pass: a stream's runs, cut at every run whose window does not depend on what precedes it
+    std::vector<RunStream> chains;
+    {
+        std::vector<uint8_t> flags(n, 1);
+        if (!bk.tail_markers(d_run_off, (uint32_t)n, d_sym, d_flags) || !bk.d2h(flags.data(), d_flags, n)) return -4;
+        for (size_t si = 0; si < streams.size(); si++) {
+            const uint32_t f = streams[si].first_run, k = streams[si].n_runs;
+            for (uint32_t r = f; r < f + k; r++) {
+                if (r == f || !flags[r]) chains.push_back(RunStream{r, 0, run_off[f]});
+                chains.back().n_runs++;
+            }
+        }
+        if (!bk.h2d(d_streams, chains.data(), sizeof(RunStream) * chains.size())) return -4;
+    }
+    if (!bk.window(d_streams, (uint32_t)chains.size(), d_run_off, d_sym, d_win, d_bad)) return -4;
     bk.mark("window");
     if (!bk.resolve(d_slices, (uint32_t)slices.size(), d_run_off, d_final_off, d_first, d_sym, d_win, bk.d_out(), d_bad)) return -4;
     bk.mark("resolve");

@@ -686,6 +686,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_L
     }
 }
 
+#ifdef CZ_EXPERIMENTS  // phase B variants that measured slower than inflate_lz_kernel<8, 0> (profiles/r1_notes.md)
 // ---------------------------------------------------------------------------------------------------------------
 // Phase B, one warp per unit, TPL tokens per lane (32 * TPL tokens per step). Same resolution rule as the token-parallel
 // branch of inflate_lz_kernel (a token is ready when the part of this step it reads lies below the first unfinished token),
@@ -1187,5 +1188,7 @@ __global__ void __launch_bounds__(W * 32, 3) inflate_lz_cta_kernel(TwoPhaseParam
         }
     }
 }
+
+#endif  // CZ_EXPERIMENTS
 
 }  // namespace czk

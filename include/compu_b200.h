@@ -138,6 +138,11 @@ int cz_inflate_segmented(const uint8_t *in, uint64_t len, uint8_t *out, uint64_t
 /* Same contracts, all pointers are device pointers on the CURRENT CUDA device, work is enqueued on `cuda_stream`
    (a cudaStream_t passed as void*) and NOT synchronised. These are what bench.py times for the roofline figure. */
 
+/* 1 when the library was built with -DCZ_EXPERIMENTS (make EXPERIMENTS=1): the kernel variants that measured slower than the
+   defaults are compiled in and the tuning knobs below can select them. The default build holds only the product kernels;
+   there the knobs accept the default configurations only and return CZ_E_STREAM for anything else. */
+int cz_has_experiments(void);
+
 /* Tuning knob (experiments): selects an inflate kernel variant; see compu_b200/csrc/inflate.cu. Default from CZ_INFLATE_CFG
    or -2,14 (two-phase: lane-per-stream token decode with 14 warps per SM, then warp-per-stream LZ77 resolution). */
 int cz_tune_inflate(int slots_per_warp, int warps_per_cta);

@@ -131,6 +131,11 @@ struct SimRunsBackend {
         cusim::launch(grid, 2 * 32, 0, inflate_lz16_kernel<2>, Q, sym);
         return true;
     }
+    bool tail_markers(const uint64_t *run_off, uint32_t n, const uint16_t *sym, uint8_t *flags) {
+        cusim::set_seed(seed++);
+        cusim::launch((n + 1) / 2, 2 * 32, 0, inflate_tail_markers_kernel<2>, run_off, n, sym, flags);
+        return true;
+    }
     bool window(const RunStream *st, uint32_t ns, const uint64_t *run_off, const uint16_t *sym, uint8_t *win, uint32_t *bad) {
         if (!ns) return true;
         cusim::set_seed(seed++);
