@@ -854,6 +854,24 @@ extern "C" int cz_inflate_segmented(const uint8_t *in, uint64_t len, uint8_t *ou
     // container header as written by cz_deflate_segmented
     if (window_bits == 15 && (in[0] != 0x78 || ((in[0] << 8 | in[1]) % 31) != 0 || (in[1] & 0x20))) return CZ_E_DATA;
     if (window_bits > 15 && (in[0] != 0x1f || in[1] != 0x8b || in[2] != 8 || in[3] != 0)) return CZ_E_DATA;
+    // On ONE device the block-parallel path decodes the stream faster than a warp per 1 MiB segment does (runs of ~32 KiB of
+    // input instead of whole segments: B200, 1 GiB gzip: 114 ms against 133 ms), so it goes first; with several devices the
+    // index shards the segments over them, and it remains the fallback.
+    if (len >= runs_min_unit_bytes() && __builtin_popcount(devices_mask ? devices_mask : 1u) == 1) {
+        const uint64_t ioff[2] = {0, len}, ooff[2] = {0, cap};
+        uint64_t got = 0, used = 0;
+        int32_t st1 = 0;
+        uint8_t done1 = 0;
+        int prev = 0;
+        cudaGetDevice(&prev);
+        const int rc1 = inflate_long_units(devices_mask ? __builtin_ctz(devices_mask) : 0, std::vector<size_t>(1, 0), in, ioff, out, ooff, &got, &st1,
+                                           &used, window_bits, &done1);
+        cudaSetDevice(prev);
+        if (rc1 == 0 && done1 && used == len) {
+            if (out_len) *out_len = got;
+            return 0;
+        }
+    }
     std::vector<uint64_t> in_off(seg_index, seg_index + n_segments + 1), out_off(n_segments + 1), lens(n_segments);
     std::vector<int32_t> st(n_segments);
     std::vector<uint32_t> chk(2 * n_segments);

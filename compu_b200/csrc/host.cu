@@ -137,8 +137,16 @@ struct InflateWork {
     bool init(int d) {
         if (dev == d && streams[0]) return true;
         dev = d;
-        for (int i = 0; i < CZ_INFLATE_STREAMS; i++)
-            if (!CZ_CUDA(cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking))) return false;
+        // sub-batches are dealt round robin, so stream i holds earlier work than stream i+1 within every round: earlier
+        // sub-batches get the higher priority, so that they FINISH first and their device-to-host copies start while the later
+        // ones still compute (the copy engine, not the SMs, bounds the end-to-end path). CZ_INFLATE_PRIO=0: equal priorities.
+        static const bool prio = [] { const char *e = getenv("CZ_INFLATE_PRIO"); return !e || atoi(e) != 0; }();
+        int lo = 0, hi = 0;  // lo = least (numerically greatest), hi = greatest priority
+        if (!prio || cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { lo = hi = 0; cudaGetLastError(); }
+        for (int i = 0; i < CZ_INFLATE_STREAMS; i++) {
+            const int p = hi + (lo - hi) * i / (CZ_INFLATE_STREAMS - 1);
+            if (!CZ_CUDA(cudaStreamCreateWithPriority(&streams[i], cudaStreamNonBlocking, p))) return false;
+        }
         return true;
     }
     ~InflateWork() {

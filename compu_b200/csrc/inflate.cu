@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <thread>
 #include <chrono>
 
 #include "host_common.h"
@@ -332,77 +333,111 @@ uint64_t runs_min_unit_bytes() { return std::max<uint64_t>(128u << 10, 2 * runs_
 // Decodes the long streams `ids` of a packed host batch on device `dev` with the block-parallel path, in batches bounded by
 // device memory. done[i] = 1 for the units it decoded (out, out_lens, statuses = Finished, in_consumed written); the others
 // are left untouched for the serial path.
+static DevicePool<CudaRunsBackend, 2> g_runs_pool;
+
+// One batch [a, b) of `ids` on backend `bk`: host -> device, the run pipeline, device -> host, results.
+static int inflate_long_batch(CudaRunsBackend *bk, const std::vector<size_t> &ids, size_t a, size_t b, const uint8_t *in,
+                              const uint64_t *in_off, uint8_t *out, const uint64_t *out_off, uint64_t *out_lens, int32_t *statuses,
+                              uint64_t *in_consumed, int window_bits, uint8_t *done) {
+    std::vector<BigUnit> units(b - a);
+    uint64_t in_bytes = 0;
+    for (size_t k = a; k < b; k++) in_bytes += runs_align(in_off[ids[k] + 1] - in_off[ids[k]] + 64);
+    if (!bk->in.reserve(in_bytes + 256)) { cudaGetLastError(); return 0; }  // no memory for this batch: the serial path takes these units
+    uint64_t o = 0;
+    bool copied = true;
+    for (size_t k = a; k < b; k++) {
+        BigUnit &U = units[k - a];
+        const size_t i = ids[k];
+        U.h_in = in + in_off[i]; U.in_len = in_off[i + 1] - in_off[i]; U.d_in_lo = o;
+        U.out_cap = out_off[i + 1] - out_off[i]; U.window_bits = window_bits;
+        U.d_out_off = out_off[i] - out_off[ids[a]];  // the caller's layout, so that neighbouring units leave in one copy
+        copied = copied && CZ_CUDA(cudaMemcpyAsync(bk->d_in() + o, U.h_in, U.in_len, cudaMemcpyHostToDevice, bk->st));
+        o += runs_align(U.in_len + 64);
+    }
+    bk->mark("start");
+    if (!copied || !CZ_CUDA(cudaStreamSynchronize(bk->st))) return CZ_E_MEM;
+    bk->mark("h2d");
+    const int rc = inflate_runs_batch(*bk, units, runs_chunk_bytes());
+    if (rc != 0) { cudaGetLastError(); return 0; }  // (out of scratch memory etc.: the serial path takes the batch)
+    bool ok = true;
+    // device -> host: consecutive decoded units whose slots are exactly full and adjacent leave in one copy
+    size_t k = a;
+    while (k < b) {
+        if (!units[k - a].ok || !units[k - a].out_len) { k++; continue; }
+        size_t e = k;
+        uint64_t bytes = units[k - a].out_len;
+        while (e + 1 < b && units[e + 1 - a].ok && units[e - a].out_len == units[e - a].out_cap && ids[e + 1] == ids[e] + 1 &&
+               units[e + 1 - a].d_out_off == units[e - a].d_out_off + units[e - a].out_cap) {
+            e++;
+            bytes = units[e - a].d_out_off + units[e - a].out_len - units[k - a].d_out_off;
+        }
+        ok = ok && CZ_CUDA(cudaMemcpyAsync(out + out_off[ids[k]], bk->d_out() + units[k - a].d_out_off, bytes, cudaMemcpyDeviceToHost, bk->st));
+        k = e + 1;
+    }
+    if (!ok || !CZ_CUDA(cudaStreamSynchronize(bk->st))) return CZ_E_MEM;
+    bk->mark("d2h");
+    for (size_t q = a; q < b; q++) {
+        const BigUnit &U = units[q - a];
+        if (!U.ok) continue;
+        const size_t i = ids[q];
+        out_lens[i] = U.out_len; statuses[i] = CZ_DECODE_FINISHED;
+        if (in_consumed) in_consumed[i] = U.in_consumed;
+        done[i] = 1;
+    }
+    return 0;
+}
+
+// Decodes the long streams `ids` of a packed host batch on device `dev` with the block-parallel path, in batches bounded by
+// device memory. done[i] = 1 for the units it decoded (out, out_lens, statuses = Finished, in_consumed written); the others
+// are left untouched for the serial path. With more than one batch, two host threads drive alternate batches on two
+// backends (own stream and buffers), so the copies of one batch overlap the kernels of the other.
 int inflate_long_units(int dev, const std::vector<size_t> &ids, const uint8_t *in, const uint64_t *in_off, uint8_t *out,
                        const uint64_t *out_off, uint64_t *out_lens, int32_t *statuses, uint64_t *in_consumed, int window_bits,
                        uint8_t *done) {
     DeviceCtx *ctx = device_ctx(dev);
     if (!ctx) return CZ_E_NO_DEVICE;
     if (ids.empty()) return 0;
-    static DevicePool<CudaRunsBackend, 1> pool;
-    if (!CZ_CUDA(cudaSetDevice(dev))) return CZ_E_MEM;
-    CudaRunsBackend *bk = pool.acquire(dev);
-    if (!bk) return CZ_E_MEM;
-    struct Lease { CudaRunsBackend *b; int dev; DevicePool<CudaRunsBackend, 1> *p; ~Lease() { p->release(dev, b); } } lease{bk, dev, &pool};
-    if (!bk->init(ctx)) return CZ_E_MEM;
-    const uint64_t batch_out = 2048ull << 20, batch_in = 1024ull << 20;
-    size_t a = 0;
-    while (a < ids.size()) {
-        // a batch: bounded by (the callers' slots as a proxy for) output and by input bytes
-        size_t b = a;
-        uint64_t in_bytes = 0, cap_bytes = 0;
-        while (b < ids.size()) {
-            const uint64_t il = in_off[ids[b] + 1] - in_off[ids[b]], ol = out_off[ids[b] + 1] - out_off[ids[b]];
-            if (b > a && (in_bytes + il > batch_in || cap_bytes + ol > batch_out ||
-                          out_off[ids[b] + 1] - out_off[ids[a]] > 2 * batch_out)) break;  // (the device buffer mirrors the callers' span)
-            in_bytes += runs_align(il + 64); cap_bytes += ol;
-            b++;
-        }
-        std::vector<BigUnit> units(b - a);
-        if (!bk->in.reserve(in_bytes + 256)) return 0;  // no memory for this batch: the serial path takes these units
-        uint64_t o = 0;
-        bool copied = true;
-        for (size_t k = a; k < b; k++) {
-            BigUnit &U = units[k - a];
-            const size_t i = ids[k];
-            U.h_in = in + in_off[i]; U.in_len = in_off[i + 1] - in_off[i]; U.d_in_lo = o;
-            U.out_cap = out_off[i + 1] - out_off[i]; U.window_bits = window_bits;
-            U.d_out_off = out_off[i] - out_off[ids[a]];  // the caller's layout, so that neighbouring units leave in one copy
-            copied = copied && CZ_CUDA(cudaMemcpyAsync(bk->d_in() + o, U.h_in, U.in_len, cudaMemcpyHostToDevice, bk->st));
-            o += runs_align(U.in_len + 64);
-        }
-        bk->mark("start");
-        if (!copied || !CZ_CUDA(cudaStreamSynchronize(bk->st))) return CZ_E_MEM;
-        bk->mark("h2d");
-        const int rc = inflate_runs_batch(*bk, units, runs_chunk_bytes());
-        if (rc == 0) {
-            bool ok = true;
-            // device -> host: consecutive decoded units whose slots are exactly full and adjacent leave in one copy
-            size_t k = a;
-            while (k < b) {
-                if (!units[k - a].ok || !units[k - a].out_len) { k++; continue; }
-                size_t e = k;
-                uint64_t bytes = units[k - a].out_len;
-                while (e + 1 < b && units[e + 1 - a].ok && units[e - a].out_len == units[e - a].out_cap && ids[e + 1] == ids[e] + 1 &&
-                       units[e + 1 - a].d_out_off == units[e - a].d_out_off + units[e - a].out_cap) {
-                    e++;
-                    bytes = units[e - a].d_out_off + units[e - a].out_len - units[k - a].d_out_off;
-                }
-                ok = ok && CZ_CUDA(cudaMemcpyAsync(out + out_off[ids[k]], bk->d_out() + units[k - a].d_out_off, bytes, cudaMemcpyDeviceToHost, bk->st));
-                k = e + 1;
+    // batches: bounded by input bytes and by (the callers' slots as a proxy for) output bytes
+    uint64_t total_in = 0;
+    for (size_t i : ids) total_in += in_off[i + 1] - in_off[i];
+    const bool small_job = total_in <= (768ull << 20);
+    const uint64_t batch_in = small_job ? (1024ull << 20) : (384ull << 20), batch_out = small_job ? (2048ull << 20) : (1024ull << 20);
+    std::vector<size_t> cut(1, 0);
+    {
+        size_t a = 0;
+        while (a < ids.size()) {
+            size_t b = a;
+            uint64_t in_bytes = 0, cap_bytes = 0;
+            while (b < ids.size()) {
+                const uint64_t il = in_off[ids[b] + 1] - in_off[ids[b]], ol = out_off[ids[b] + 1] - out_off[ids[b]];
+                if (b > a && (in_bytes + il > batch_in || cap_bytes + ol > batch_out ||
+                              out_off[ids[b] + 1] - out_off[ids[a]] > 2 * batch_out)) break;  // (the device buffer mirrors the callers' span)
+                in_bytes += il; cap_bytes += ol;
+                b++;
             }
-            if (!ok || !CZ_CUDA(cudaStreamSynchronize(bk->st))) return CZ_E_MEM;
-            bk->mark("d2h");
-            for (size_t k = a; k < b; k++) {
-                const BigUnit &U = units[k - a];
-                if (!U.ok) continue;
-                const size_t i = ids[k];
-                out_lens[i] = U.out_len; statuses[i] = CZ_DECODE_FINISHED;
-                if (in_consumed) in_consumed[i] = U.in_consumed;
-                done[i] = 1;
-            }
-        } else cudaGetLastError();  // (out of scratch memory etc.: the serial path takes the batch)
-        a = b;
+            cut.push_back(b);
+            a = b;
+        }
     }
+    const size_t nb = cut.size() - 1;
+    const int nworkers = nb > 1 ? 2 : 1;
+    std::vector<int> rcs(nworkers, 0);
+    auto worker = [&](int w) {
+        if (!CZ_CUDA(cudaSetDevice(dev))) { rcs[w] = CZ_E_MEM; return; }
+        CudaRunsBackend *bk = g_runs_pool.acquire(dev);
+        if (!bk) { rcs[w] = CZ_E_MEM; return; }
+        if (!bk->init(ctx)) rcs[w] = CZ_E_MEM;
+        for (size_t k = (size_t)w; k < nb && !rcs[w]; k += (size_t)nworkers)
+            rcs[w] = inflate_long_batch(bk, ids, cut[k], cut[k + 1], in, in_off, out, out_off, out_lens, statuses, in_consumed, window_bits, done);
+        g_runs_pool.release(dev, bk);
+    };
+    if (nworkers == 1) worker(0);
+    else {
+        std::thread t(worker, 1);
+        worker(0);
+        t.join();
+    }
+    for (int r : rcs) if (r) return r;
     return 0;
 }
 
