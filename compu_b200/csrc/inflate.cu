@@ -228,7 +228,7 @@ static int par_decode_off() {
 struct CudaRunsBackend {
     DeviceCtx *ctx = nullptr;
     cudaStream_t st = nullptr;
-    DevBuf in, out, arena;
+    DevBuf in, out, arena, tokbuf;
     size_t used = 0;
     int per_sm_tok = 0, per_sm_lz16 = 0;
     bool configured = false;
@@ -258,6 +258,7 @@ struct CudaRunsBackend {
     void scratch_reset() { used = 0; }
     bool scratch_need(size_t total) { return arena.reserve(total + 4096); }
     bool out_need(size_t bytes) { return out.reserve(bytes); }
+    void *tok_buffer(size_t bytes) { return tokbuf.reserve(bytes + 256) ? tokbuf.p : nullptr; }
     void *scratch(size_t bytes) {
         const size_t a = (used + 255) & ~(size_t)255;
         if (a + bytes > arena.cap) { set_error("internal: run scratch arena too small"); return nullptr; }

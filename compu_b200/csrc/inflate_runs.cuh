@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_L
         const TokMeta m = Q.meta[unit];
         uint16_t *S = sym + (o0 - P.out_off[0]);             // symbols of this run
         const uint8_t *ib = P.in + Q.runs[unit].in_lo;        // stored runs reference the stream's input
-        const uint32_t *tok = Q.tok + tok_word_off(o0 - P.out_off[0], unit);
+        const uint32_t *tok = Q.runs[unit].tok_cap ? Q.tok + Q.runs[unit].tok_off : Q.tok + tok_word_off(o0 - P.out_off[0], unit);
         const uint32_t ntok = m.ntok;
         uint64_t opos = 0;
         uint32_t ti = 0;

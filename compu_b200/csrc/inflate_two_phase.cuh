@@ -49,11 +49,14 @@ struct RunDesc {
     uint64_t target_bit;  // stop at the first block boundary >= this (UINT64_MAX: run to the end of the stream)
     uint32_t mid_stream;  // 1: starts at a block header inside the stream (no container header, distances may reach before the run)
     uint32_t pad;
+    uint64_t tok_off;     // tok_cap != 0: the run's token area is Q.tok[tok_off, tok_off + tok_cap) — sizes are not known yet when a
+    uint64_t tok_cap;     // run is decoded once only, so the area is bounded by the run's COMPRESSED size; a run that needs more
+                          // (it ran past a false next candidate) stops emitting, keeps counting and reports tok_overflow
 };
 struct RunResult {
     uint64_t end_bit;     // where the run stopped (a block boundary, or the end of the final block)
     uint32_t final_block; // 1: the run ended with the stream's final block
-    uint32_t pad;
+    uint32_t tok_overflow; // 1: the token area was too small: sizes and positions are valid, the tokens are not
 };
 #define CZK_ST_RUN_END 4  // phase A, run mode: stopped at the target boundary (internal status, never reaches the caller)
 
@@ -114,8 +117,10 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
     uint64_t run_start = 0, run_target = ~0ull;  // run mode
     bool run_mid = false;
 
-    constexpr bool emit = EMIT;
-#define CZK_PUT(x) do { if (emit) *tp++ = (x); } while (0)
+    bool emit = EMIT;                 // (run mode switches it off when a run outgrows its token area)
+    uint32_t *tp_end = nullptr;       // run mode with a bounded token area: its end
+    uint32_t tok_overflow = 0;
+#define CZK_PUT(x) do { if (emit) *tp = (x); tp++; } while (0)  // (words are counted even when nothing is stored)
 #define CZK_FLUSH_LIT() do { if (nlit) { CZK_PUT(CZK_TOK_LIT | (nlit << 24) | lit); lit = 0; nlit = 0; } } while (0)
 
     for (;;) {
@@ -131,7 +136,12 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
                 const uint64_t o0 = P.out_off[unit], o1 = P.out_off[unit + 1];
                 in_base = P.in + i0; in_len = i1 - i0;
                 cap = o1 - o0; pos = 0;
-                tp0 = tp = emit ? Q.tok + tok_word_off(o0 - P.out_off[0], unit) : nullptr;
+                emit = EMIT; tok_overflow = 0; tp_end = nullptr;
+                tp0 = tp = emit ? Q.tok + tok_word_off(o0 - P.out_off[0], unit) : (uint32_t *)nullptr + 1024;
+                if (EMIT && Q.runs && Q.runs[unit].tok_cap) {
+                    tp0 = tp = Q.tok + Q.runs[unit].tok_off;
+                    tp_end = tp + Q.runs[unit].tok_cap;
+                }
                 lit = 0; nlit = 0; bfinal = 0; result = 0; expect = 0;
                 br.init(in_base, in_len);
                 st = SS_HEADER;
@@ -226,6 +236,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
         if (st == SS_DECODE) {
             int budget = CZK_LC_BUDGET;
             const int64_t pos_safe = (int64_t)cap - 258;
+            if (EMIT && tp_end && emit && tp_end - tp < 2 * CZK_LC_BUDGET + 8) { emit = false; tok_overflow = 1; }
             // ---- fast loop. While three more input words and 258 bytes of capacity remain, none of the end-of-input /
             // end-of-slot conditions can occur (one symbol takes at most 48 bits and 258 bytes): no masking of the unit's
             // last word, no overrun tests, 32-bit position arithmetic, and the only exits are the ones below. Everything
@@ -365,6 +376,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
 
         // ---- (6) stored blocks: short runs become literal tokens, longer ones a reference into the input
         if (st == SS_STORED) {
+            if (EMIT && tp_end && emit && tp_end - tp < 16) { emit = false; tok_overflow = 1; }
             const uint64_t ipos = br.consumed() >> 3;
             int err = -1;
             uint32_t n = stored_len;
@@ -418,6 +430,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
 
         // ---- (8) hand over to phase B
         if (st == SS_FINISH) {
+            if (EMIT && tp_end && emit && nlit && tp_end - tp < 2) { emit = false; tok_overflow = 1; }
             CZK_FLUSH_LIT();
             TokMeta m;
             m.ntok = (uint32_t)(tp - tp0);
@@ -430,7 +443,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
                 RunResult rr;
                 rr.end_bit = br.consumed();
                 rr.final_block = result == ST_FINISHED ? 1u : 0u;
-                rr.pad = 0;
+                rr.tok_overflow = tok_overflow;
                 Q.run_res[unit] = rr;
             }
             if (P.in_consumed) {

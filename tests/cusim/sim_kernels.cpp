@@ -102,7 +102,8 @@ struct SimRunsBackend {
     void scratch_reset() { used = 0; }
     bool scratch_need(size_t total) { if (total > arena.size()) arena.resize(total); return true; }
     bool out_need(size_t bytes) { out_store.assign(bytes, 0xEE); out = out_store.data(); return true; }
-    std::vector<uint8_t> out_store;
+    std::vector<uint8_t> out_store, tok_store;
+    void *tok_buffer(size_t bytes) { tok_store.assign(bytes + 64, 0xDB); return tok_store.data(); }
     void *scratch(size_t bytes) {
         const size_t a = (used + 255) & ~(size_t)255;
         if (a + bytes + 256 > arena.size()) return nullptr;

@@ -72,3 +72,16 @@ def test_sim_runs_decline_what_they_cannot_prove(alice):
     assert not ok[1] and not ok[3] and not ok[4]
     assert (not ok[2]) or outs[2] != d  # a flipped bit either breaks the chain / the check ... (it must never pass as the original)
     assert not ok[2]
+
+
+def test_sim_runs_dense_tokens_are_emitted_again_with_exact_room(alice):
+    """A run is decoded once, into a token area bounded by its COMPRESSED size (2 words per byte). Huffman-only output of a
+    two-symbol source has ~1 bit per literal = 2.7 token words per compressed byte: those runs outgrow their area, keep
+    counting, and are emitted again with exactly the room they need. The result must be the same bytes."""
+    rng = random.Random(99)
+    d = bytes(98 if rng.random() < 0.03 else 97 for _ in range(400000))
+    s = zcomp(d, 6, 15, 2)  # Z_HUFFMAN_ONLY: ~1.03 bits per literal
+    assert len(s) < len(d) // 7
+    outs, ok, lens, cons, nruns = simlib.sim_inflate_runs([s, zcomp(alice * 2, 6, 15)], [len(d), 2 * len(alice)], 15, chunk_bytes=4096, seed=17)
+    assert ok[0] and outs[0] == d and cons[0] == len(s)
+    assert ok[1] and outs[1] == alice * 2
