@@ -81,7 +81,36 @@ __host__ __device__ inline uint64_t tok_word_off(uint64_t out_off, uint64_t unit
 #ifndef CZK_LZ_MINB
 #define CZK_LZ_MINB 4  // 64 registers: 32 warps per SM (5: 48 registers, 40 warps: 33.3 ms; 6: spills: 40 ms; measured on cfg2)
 #endif
-#define CZK_LZ_SHORT 12  // phase B (token-parallel): matches up to this long are copied by their own lane (8/12/16/24/32 measured: 33.9/32.6/34.0/35.5/38.0 ms)
+// Phase A reads every stream word by word, one lane per stream: L1 (22 KB beside the slots) cannot keep 448 lines, so each
+// load is an L2 access, and a DRAM access whenever its sector is new. The fetch-size hint makes one DRAM access bring the next
+// CZK_TOK_L2_FETCH bytes of the lane's stream into L2 (0: plain __ldg).
+#ifndef CZK_TOK_L2_FETCH
+#define CZK_TOK_L2_FETCH 256
+#endif
+__device__ __forceinline__ uint32_t czk_ldg_stream(const uint32_t *p) {
+#if defined(__CUDA_ARCH__) && CZK_TOK_L2_FETCH == 256
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::256B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#elif defined(__CUDA_ARCH__) && CZK_TOK_L2_FETCH == 128
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::128B.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
+#ifndef CZK_LZ_WIDE
+#define CZK_LZ_WIDE 1  // phase B: short matches read their source as aligned 8-byte words (0: one load per byte)
+#endif
+#ifndef CZK_LZ_PF
+#define CZK_LZ_PF 0  // phase B look-ahead: 0 off, 1 prefetch the next group's sources into L2, 2 into L1
+#endif
+#ifndef CZK_LZ_SHORT
+#define CZK_LZ_SHORT 12
+#endif
+// phase B (token-parallel): matches up to this long are copied by their own lane (8/12/16/24/32 measured: 33.9/32.6/34.0/35.5/38.0 ms)
 
 // EMIT = false: counting only (no token is written; sizes, statuses and end positions are the result).
 template <int WARPS, bool EMIT = true>
@@ -257,7 +286,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
                         cnt += 32;
                         widx++;
                         nextw = nextw2;
-                        nextw2 = widx + 1 < wend ? __ldg(words + widx + 1) : 0u;
+                        nextw2 = widx + 1 < wend ? czk_ldg_stream(words + widx + 1) : 0u;
                     }
                     uint32_t v = __brev((uint32_t)buf) >> 16;
                     const uint32_t cl = lc_code_len(v, llim);
@@ -286,7 +315,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
                         c2 += 32;
                         w2++;
                         n1 = n2;
-                        n2 = w2 + 1 < wend ? __ldg(words + w2 + 1) : 0u;
+                        n2 = w2 + 1 < wend ? czk_ldg_stream(words + w2 + 1) : 0u;
                     }
                     v = __brev((uint32_t)b2) >> 16;
                     const uint32_t dcl = lc_code_len(v, dlim);
@@ -491,10 +520,31 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_L
         uint64_t opos = 0, ck_pos = 0;
         uint32_t adler = 1, crc = 0;
         uint32_t ti = 0;
+#if CZK_LZ_PF
+        // Look-ahead (H == 0): the tokens of the next two groups travel in registers, and while group g is resolved the far
+        // back-references of group g+1 are prefetched — the warp used to wait twice per group for a DRAM / L2 round trip
+        // (token load, then the sources; the windows of the streams in flight exceed L2), now both are requested one group early.
+        uint32_t tA = 0, tB = 0;
+        bool la_ok = false;
+#endif
         while (ti < ntok) {
+#if CZK_LZ_PF
+            uint32_t t_raw;
+            if (la_ok) { t_raw = tA; tA = tB; }
+            else {
+                t_raw = ti + lane < ntok ? tok[ti + lane] : CZK_TOK_STORED;
+                tA = ti + 32 + lane < ntok ? tok[ti + 32 + lane] : CZK_TOK_STORED;
+            }
+            tB = ti + 64 + lane < ntok ? tok[ti + 64 + lane] : CZK_TOK_STORED;
+            la_ok = true;
+#else
             const uint32_t t_raw = ti + lane < ntok ? tok[ti + lane] : CZK_TOK_STORED;  // past the end: acts as a stop mark
+#endif
             const uint32_t stopm = __ballot_sync(CZK_FULL, (t_raw >> 30) == 3u);
             const uint32_t nt = stopm ? (uint32_t)__ffs(stopm) - 1u : 32u;  // ordinary tokens before the first stored mark
+#if CZK_LZ_PF
+            if (nt < 32) la_ok = false;  // the next group does not start 32 words on: load it afresh
+#endif
             if (nt) {
                 const uint32_t t = lane < nt ? t_raw : 0u;
                 const uint32_t tl = (t >> 31) ? ((t >> 24) & 3u) : (t & 0x1ffu);
@@ -507,6 +557,28 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_L
                 }
                 const uint32_t total = __shfl_sync(CZK_FULL, pos, 31);
                 pos -= tl;
+#if CZK_LZ_PF
+                if (H == 0 && nt == 32 && !__any_sync(CZK_FULL, (tA >> 30) == 3u)) {
+                    const uint32_t la_len = (tA >> 31) ? ((tA >> 24) & 3u) : (tA & 0x1ffu);
+                    uint32_t pa = la_len;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        uint32_t v = __shfl_up_sync(CZK_FULL, pa, d);
+                        if ((int)lane >= d) pa += v;
+                    }
+                    pa -= la_len;
+                    if (!(tA >> 31)) {
+                        const uint8_t *src = ob + opos + total + pa - ((tA >> 9) & 0xffffu);
+#if defined(__CUDA_ARCH__) && CZK_LZ_PF == 2
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(src));
+#elif defined(__CUDA_ARCH__)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+#else
+                        (void)src;
+#endif
+                    }
+                }
+#endif
                 if constexpr (H <= 0) {
                     constexpr int SHORT = H == 0 ? CZK_LZ_SHORT : -H;
                     // ---- token-parallel resolution: lane = token. A token is copied by its own lane (literals; matches of up to
@@ -538,11 +610,35 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_L
                                 if (tl > 2) d[2] = (uint8_t)(t >> 16);
                             } else {
                                 const uint8_t *sp = obp + src0;
-                                uint32_t bb[SHORT];
+                                if constexpr (SHORT <= 16 && CZK_LZ_WIDE) {
+                                    // The source is read as aligned 8-byte words (two on average 1.5 of them instead of one load per
+                                    // byte): the L1 data pipe handles one line per lane and load instruction, and it was 73 % busy
+                                    // (profiles/r1_inflate_lz_cfg2_final_ncu.md). A word holds at least one wanted byte, so it lies in
+                                    // a mapped page; the bytes around the source that other lanes may be writing are discarded.
+                                    const uintptr_t a = (uintptr_t)sp;
+                                    const uint32_t o = (uint32_t)a & 7u;
+                                    const uint2 *q = (const uint2 *)(a - o);
+                                    const uint32_t need = o + tl;
+                                    uint2 q0 = q[0], q1 = make_uint2(0u, 0u), q2 = make_uint2(0u, 0u);
+                                    if (need > 8) q1 = q[1];
+                                    if (need > 16) q2 = q[2];
+                                    uint32_t w0 = q0.x, w1 = q0.y, w2 = q1.x, w3 = q1.y, w4 = q2.x, w5 = q2.y;
+                                    if (o & 4u) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+                                    const uint32_t sh = (o & 3u) * 8u;
+                                    uint32_t b[4];
+                                    b[0] = __funnelshift_r(w0, w1, sh);
+                                    b[1] = __funnelshift_r(w1, w2, sh);
+                                    b[2] = __funnelshift_r(w2, w3, sh);
+                                    b[3] = __funnelshift_r(w3, w4, sh);
 #pragma unroll
-                                for (int k = 0; k < SHORT; k++) bb[k] = k < (int)tl ? sp[k] : 0u;
+                                    for (int k = 0; k < SHORT; k++) if (k < (int)tl) d[k] = (uint8_t)(b[k >> 2] >> (8 * (k & 3)));
+                                } else {
+                                    uint32_t bb[SHORT];
 #pragma unroll
-                                for (int k = 0; k < SHORT; k++) if (k < (int)tl) d[k] = (uint8_t)bb[k];
+                                    for (int k = 0; k < SHORT; k++) bb[k] = k < (int)tl ? sp[k] : 0u;
+#pragma unroll
+                                    for (int k = 0; k < SHORT; k++) if (k < (int)tl) d[k] = (uint8_t)bb[k];
+                                }
                             }
                         }
                         uint32_t cm = __ballot_sync(CZK_FULL, ready && coop);
