@@ -218,7 +218,9 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
     const size_t nsub = cut.size() - 1;
     // big units (megabytes in one stream) go to the warp-per-stream kernel, the rest to the two-phase path
     // (a lane decodes ~4 MB/s, a warp ~26 MB/s: beyond ~256 KiB of output the lane-per-stream path becomes the tail of the batch)
-    const uint64_t big_in = 96u << 10, big_out = 256u << 10;
+    // A shard of few units leaves most lanes of the two-phase path idle anyway: there the warp-per-stream kernel takes over earlier.
+    const bool few = n < 16384;
+    const uint64_t big_in = few ? 40u << 10 : 96u << 10, big_out = few ? 96u << 10 : 256u << 10;
     static const long fast_mb = [] { const char *e = getenv("CZ_INFLATE_FAST_MB"); return e ? atol(e) : 0l; }();
     const uint64_t fast_head = oe - ob >= (2048ull << 20) ? (uint64_t)fast_mb << 20 : 0;
     std::vector<uint32_t> ids;  // per sub-batch: [small ids..., big ids...], relative to the sub-batch's first unit
@@ -350,38 +352,25 @@ int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint
         if (!device_ctx(d)) return CZ_E_NO_DEVICE;
     std::vector<size_t> cuts;
     split_by_bytes(n, in_off, (int)devs.size(), cuts);
-    // Long streams first: the block-parallel path (inflate_runs.cuh) decodes them run by run on their shard's device. What it
-    // declines (errors, truncation, slots that are too small) stays in the batch for the serial kernels below.
-    std::vector<uint8_t> skip;
+    // Long streams take the block-parallel path (inflate_runs.cuh), run by run on their shard's device, WHILE the ordinary units
+    // of every shard go through the serial kernels: pass 1 enqueues the shards without the long units (copies and kernels are
+    // asynchronous), the host then drives the long units on other streams, and whatever the block-parallel path declines (errors,
+    // truncation, slots that are too small) goes through the serial kernels in a second pass.
     struct Done { size_t i; uint64_t len, cons; int32_t st; };
     std::vector<Done> done;
+    std::vector<uint8_t> skip;        // pass 1: the long units
+    std::vector<uint8_t> declined;    // long units the block-parallel path left alone
+    std::vector<std::vector<size_t>> long_ids(devs.size());
     static const bool no_runs = getenv("CZ_NO_RUNS") != nullptr || getenv("CZ_NO_SPLIT") != nullptr;
     if (!segment_mode && !checks && !no_runs) {
-        std::vector<std::vector<size_t>> long_ids(devs.size());
         bool any = false;
         for (size_t k = 0; k < devs.size(); k++)
             for (size_t i = cuts[k]; i < cuts[k + 1]; i++)
                 if (in_off[i + 1] - in_off[i] >= runs_min_unit_bytes()) { long_ids[k].push_back(i); any = true; }
         if (any) {
             skip.assign(n, 0);
-            std::vector<uint64_t> cons(n, 0);
-            std::vector<int> rcs(devs.size(), 0);
-            auto work = [&](size_t k) {
-                rcs[k] = inflate_long_units(devs[k], long_ids[k], in, in_off, out, out_off, out_lens, statuses, cons.data(), window_bits, skip.data());
-            };
-            std::vector<std::thread> th;
-            for (size_t k = 1; k < devs.size(); k++)
-                if (!long_ids[k].empty()) th.emplace_back(work, k);
-            if (!long_ids[0].empty()) work(0);
-            for (auto &t : th) t.join();
-            for (size_t k = 0; k < devs.size(); k++) {
-                if (rcs[k]) return rcs[k];
-                for (size_t i : long_ids[k]) {
-                    g_split_tried++;
-                    if (skip[i]) { g_split_ok++; done.push_back(Done{i, out_lens[i], cons[i], statuses[i]}); }
-                }
-            }
-            if (done.empty()) skip.clear();
+            for (size_t k = 0; k < devs.size(); k++)
+                for (size_t i : long_ids[k]) skip[i] = 1;
         }
     }
     // one work object (streams, device and pinned buffers) per device, borrowed from a bounded per-device pool
@@ -395,30 +384,75 @@ int inflate_batch_host(size_t n, const uint8_t *in, const uint64_t *in_off, uint
         if (!(works[d] = pool.acquire(d))) { set_error("out of memory"); return CZ_E_MEM; }
     int prev = 0;
     cudaGetDevice(&prev);
+    struct RestoreDev { int d; ~RestoreDev() { cudaSetDevice(d); } } restore_dev{prev};
     int rc = 0;
-    // enqueue every shard first (copies and kernels of different devices overlap), then wait for all
+    // waits for the shards of one pass and collects the per-unit results of the units that pass handled
+    auto finish_pass = [&](const uint8_t *skipped) {
+        for (size_t k = 0; k < devs.size(); k++) {
+            if (!works[devs[k]]->streams[0]) continue;
+            cudaSetDevice(devs[k]);
+            InflateWork &w = *works[devs[k]];
+            if (!w.sync_all() && !rc) rc = CZ_E_MEM;
+            if (!rc && w.res_n) {
+                if (!skipped) {
+                    memcpy(out_lens + w.res_u0, w.res_lens, 8 * w.res_n);
+                    memcpy(statuses + w.res_u0, w.res_stat, 4 * w.res_n);
+                    if (in_consumed) memcpy(in_consumed + w.res_u0, w.res_cons, 8 * w.res_n);
+                    if (checks) memcpy(checks + 2 * w.res_u0, w.res_chk, 8 * w.res_n);
+                } else {
+                    for (size_t j = 0; j < w.res_n; j++) {
+                        const size_t i = w.res_u0 + j;
+                        if (skipped[i]) continue;
+                        out_lens[i] = w.res_lens[j];
+                        statuses[i] = w.res_stat[j];
+                        if (in_consumed) in_consumed[i] = w.res_cons[j];
+                        if (checks) { checks[2 * i] = w.res_chk[2 * j]; checks[2 * i + 1] = w.res_chk[2 * j + 1]; }
+                    }
+                }
+            }
+            w.res_n = 0;
+        }
+    };
+    // pass 1: enqueue every shard (copies and kernels of different devices overlap) ...
     for (size_t k = 0; k < devs.size() && !rc; k++)
         rc = inflate_shard(*works[devs[k]], devs[k], cuts[k], cuts[k + 1], in, in_off, out, out_off, out_lens, statuses,
                            in_consumed, window_bits, segment_mode, checks, skip.empty() ? nullptr : skip.data());
-    for (size_t k = 0; k < devs.size(); k++) {
-        if (!works[devs[k]]->streams[0]) continue;
-        cudaSetDevice(devs[k]);
-        InflateWork &w = *works[devs[k]];
-        if (!w.sync_all() && !rc) rc = CZ_E_MEM;
-        if (!rc && w.res_n) {
-            memcpy(out_lens + w.res_u0, w.res_lens, 8 * w.res_n);
-            memcpy(statuses + w.res_u0, w.res_stat, 4 * w.res_n);
-            if (in_consumed) memcpy(in_consumed + w.res_u0, w.res_cons, 8 * w.res_n);
-            if (checks) memcpy(checks + 2 * w.res_u0, w.res_chk, 8 * w.res_n);
+    // ... the long units meanwhile (one host thread per device) ...
+    if (!skip.empty() && !rc) {
+        std::vector<uint8_t> ok(n, 0);
+        std::vector<uint64_t> cons(n, 0);
+        std::vector<int> rcs(devs.size(), 0);
+        auto work = [&](size_t k) {
+            rcs[k] = inflate_long_units(devs[k], long_ids[k], in, in_off, out, out_off, out_lens, statuses, cons.data(), window_bits, ok.data());
+        };
+        std::vector<std::thread> th;
+        for (size_t k = 1; k < devs.size(); k++)
+            if (!long_ids[k].empty()) th.emplace_back(work, k);
+        if (!long_ids[0].empty()) work(0);
+        for (auto &t : th) t.join();
+        for (size_t k = 0; k < devs.size(); k++) {
+            if (rcs[k] && !rc) rc = rcs[k];
+            for (size_t i : long_ids[k]) {
+                g_split_tried++;
+                if (ok[i]) { g_split_ok++; done.push_back(Done{i, out_lens[i], cons[i], statuses[i]}); }
+                else { if (declined.empty()) declined.assign(n, 1); declined[i] = 0; }  // (declined[] is a skip list: 0 = decode it)
+            }
         }
-        w.res_n = 0;
     }
+    // ... and wait
+    finish_pass(skip.empty() ? nullptr : skip.data());
     for (const Done &d : done) {
         out_lens[d.i] = d.len;
         statuses[d.i] = d.st;
         if (in_consumed) in_consumed[d.i] = d.cons;
     }
-    cudaSetDevice(prev);
+    // pass 2: what the block-parallel path declined
+    if (!declined.empty() && !rc) {
+        for (size_t k = 0; k < devs.size() && !rc; k++)
+            rc = inflate_shard(*works[devs[k]], devs[k], cuts[k], cuts[k + 1], in, in_off, out, out_off, out_lens, statuses,
+                               in_consumed, window_bits, segment_mode, checks, declined.data());
+        finish_pass(declined.data());
+    }
     return rc;
 }
 

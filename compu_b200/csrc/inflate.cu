@@ -326,10 +326,10 @@ struct CudaRunsBackend {
 };
 
 static uint64_t runs_chunk_bytes() {
-    static const uint64_t v = [] { const char *e = getenv("CZ_RUN_CHUNK_KB"); long k = e ? atol(e) : 0; return k >= 4 ? (uint64_t)k << 10 : (uint64_t)(32u << 10); }();
+    static const uint64_t v = [] { const char *e = getenv("CZ_RUN_CHUNK_KB"); long k = e ? atol(e) : 0; return k >= 4 ? (uint64_t)k << 10 : (uint64_t)(16u << 10); }();
     return v;
 }
-uint64_t runs_min_unit_bytes() { return std::max<uint64_t>(128u << 10, 2 * runs_chunk_bytes()); }
+uint64_t runs_min_unit_bytes() { return std::max<uint64_t>(64u << 10, 4 * runs_chunk_bytes()); }
 
 // Decodes the long streams `ids` of a packed host batch on device `dev` with the block-parallel path, in batches bounded by
 // device memory. done[i] = 1 for the units it decoded (out, out_lens, statuses = Finished, in_consumed written); the others

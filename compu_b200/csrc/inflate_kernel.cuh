@@ -439,13 +439,38 @@ __device__ inline int parse_gzip_header(BitReader &br) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Warp-cooperative checksum of out[from, to). adler/crc are running (finalised-form) values, uniform across the warp.
+// sum of the four bytes of w, and sum of j * byte j (j = 0..3)
+__device__ __forceinline__ void adler_word(uint32_t w, uint32_t &s, uint32_t &ws) {
+#if defined(__CUDA_ARCH__)
+    s = __dp4a(w, 0x01010101u, 0u);
+    ws = __dp4a(w, 0x03020100u, 0u);
+#else
+    const uint32_t b0 = w & 0xff, b1 = (w >> 8) & 0xff, b2 = (w >> 16) & 0xff, b3 = w >> 24;
+    s = b0 + b1 + b2 + b3;
+    ws = b1 + 2 * b2 + 3 * b3;
+#endif
+}
+
+// Adler-32 of n <= 8192 bytes on top of `adler`, by the whole warp: a1 = sum b[k], a2 = sum (n - k) b[k]. The 16-byte aligned
+// body is read as uint4 (16 bytes per lane and load, byte sums on the DP4A pipe), the unaligned head and the tail byte-wise.
 __device__ inline uint32_t warp_adler32(uint32_t adler, const uint8_t *p, uint32_t n, uint32_t lane) {
-    // n <= 8192
     uint32_t a1 = 0, a2 = 0;
-    for (uint32_t k = lane; k < n; k += 32) {
-        uint32_t b = p[k];
-        a1 += b;
-        a2 += (n - k) * b;
+    uint32_t head = (uint32_t)((0 - (uintptr_t)p) & 15);
+    if (head > n) head = n;
+    const uint32_t body = (n - head) & ~15u;
+    if (lane < head) { const uint32_t b = p[lane]; a1 = b; a2 = (n - lane) * b; }
+    for (uint32_t k = head + 16 * lane; k < head + body; k += 512) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(p + k);
+        uint32_t s0, s1, s2, s3, w0, w1, w2, w3;
+        adler_word(v.x, s0, w0); adler_word(v.y, s1, w1); adler_word(v.z, s2, w2); adler_word(v.w, s3, w3);
+        const uint32_t S = s0 + s1 + s2 + s3;
+        a1 += S;
+        // sum over the 16 bytes of (n - k - j) b[j] = (n - k) S - sum j b[j]
+        a2 += (n - k) * S - (w0 + w1 + w2 + w3 + 4 * s1 + 8 * s2 + 12 * s3);
+    }
+    {
+        const uint32_t k = head + body + lane;
+        if (k < n) { const uint32_t b = p[k]; a1 += b; a2 += (n - k) * b; }  // (fewer than 16 bytes are left)
     }
     a2 %= CZK_ADLER_BASE;
     a1 = __reduce_add_sync(CZK_FULL, a1);

@@ -517,6 +517,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_L
         const bool by_kind = P.segment_mode || (P.checks && m.wrap == 0);  // raw units asked for checks: pieces of a longer stream
         const bool want_adler = by_kind ? (P.check_kind & 1) : m.wrap == 1;
         const bool want_crc = by_kind ? (P.check_kind & 2) : (m.wrap & 3) == 2;
+        const bool want_ck = want_adler || want_crc;
         uint64_t opos = 0, ck_pos = 0;
         uint32_t adler = 1, crc = 0;
         uint32_t ti = 0;
@@ -755,7 +756,7 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_L
                 ti += 3;
             }
             // ---- checksums over freshly written output (L1/L2 hits), in pieces
-            if ((want_adler || want_crc) && (opos - ck_pos >= 8192 || ti >= ntok)) {
+            if (want_ck && ((uint32_t)(opos - ck_pos) >= 8192u || ti >= ntok)) {
                 uint64_t to = opos;
                 if (ti < ntok) to = ck_pos + ((to - ck_pos) & ~(uint64_t)127);  // keep CRC pieces at 128 B until the end
                 if (want_adler) {
