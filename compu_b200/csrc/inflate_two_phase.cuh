@@ -101,6 +101,9 @@ __device__ __forceinline__ uint32_t czk_ldg_stream(const uint32_t *p) {
 #endif
 }
 
+#ifndef CZK_LZ_ABL
+#define CZK_LZ_ABL 0
+#endif
 #ifndef CZK_LZ_WIDE
 #define CZK_LZ_WIDE 1  // phase B: short matches read their source as aligned 8-byte words (0: one load per byte)
 #endif
@@ -620,9 +623,14 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_L
                                     const uint32_t o = (uint32_t)a & 7u;
                                     const uint2 *q = (const uint2 *)(a - o);
                                     const uint32_t need = o + tl;
+#if CZK_LZ_ABL == 1  // ablation (timing experiments only, wrong output): no source loads
+                                    uint2 q0 = make_uint2(o, need), q1 = make_uint2(0u, 0u), q2 = make_uint2(0u, 0u);
+                                    (void)q;
+#else
                                     uint2 q0 = q[0], q1 = make_uint2(0u, 0u), q2 = make_uint2(0u, 0u);
                                     if (need > 8) q1 = q[1];
                                     if (need > 16) q2 = q[2];
+#endif
                                     uint32_t w0 = q0.x, w1 = q0.y, w2 = q1.x, w3 = q1.y, w4 = q2.x, w5 = q2.y;
                                     if (o & 4u) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
                                     const uint32_t sh = (o & 3u) * 8u;
@@ -631,8 +639,12 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_L
                                     b[1] = __funnelshift_r(w1, w2, sh);
                                     b[2] = __funnelshift_r(w2, w3, sh);
                                     b[3] = __funnelshift_r(w3, w4, sh);
+#if CZK_LZ_ABL == 2  // ablation: one store per token instead of one per byte
+                                    d[0] = (uint8_t)(b[0] ^ b[1] ^ b[2] ^ b[3]);
+#else
 #pragma unroll
                                     for (int k = 0; k < SHORT; k++) if (k < (int)tl) d[k] = (uint8_t)(b[k >> 2] >> (8 * (k & 3)));
+#endif
                                 } else {
                                     uint32_t bb[SHORT];
 #pragma unroll
