@@ -148,17 +148,27 @@ __global__ void __launch_bounds__(128) inflate_candidates_kernel(const uint8_t *
     uint32_t qn = 0;
     // Only ~11 % of the offsets pass the first filter, but with 32 offsets per step some lane nearly always does, and the warp paid
     // for the second filter at every step. The survivors are queued instead and examined 32 at a time, all lanes busy.
-    for (uint64_t base = ch.lo_bit; found == ~0ull; base += 32) {
-        const bool more = base < ch.hi_bit;
+    // The scan itself runs on 32-bit offsets relative to the word that holds the chunk's first bit, one (warp-uniform) word load
+    // per step: lane l examines the 17 bits at bit l of the 64-bit window [w0, w1].
+    const uint64_t word0 = ch.lo_bit >> 5;                                   // first word of the scan
+    const uint32_t first = (uint32_t)(ch.lo_bit & 31);                       // offsets below this lie before the chunk
+    uint64_t last64 = ch.hi_bit;                                             // offsets >= last are out: end of the chunk, or too
+    if (ch.end_bit < 17 + 57 + 14) last64 = 0;                               // close to the end of the stream for a header
+    else if (ch.end_bit - (17 + 57 + 14) + 1 < last64) last64 = ch.end_bit - (17 + 57 + 14) + 1;
+    const uint32_t last = last64 > (word0 << 5) ? (uint32_t)(last64 - (word0 << 5)) : 0u;   // (a chunk is far below 2^32 bits)
+    const uint32_t span = (uint32_t)(ch.hi_bit - (word0 << 5));
+    const uint32_t *wp = words + word0;
+    uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
+    for (uint32_t rel = 0; found == ~0ull; rel += 32) {
+        const bool more = rel < span;
         if (more) {
-            const uint64_t b = base + lane;
-            bool ok = b < ch.hi_bit && b + 17 + 57 + 14 <= ch.end_bit;
-            if (ok) {
-                const uint32_t h = cand_bits(words, b, 17);
-                ok = (h & 7u) == 4u && ((h >> 3) & 31) <= 29 && ((h >> 8) & 31) <= 29;  // BFINAL = 0, BTYPE = 10, HLIT / HDIST in range
-            }
+            const uint32_t r = rel + lane;
+            const uint32_t h = __funnelshift_r(w0, w1, lane) & 0x1ffffu;
+            const bool ok = r >= first && r < last && (h & 7u) == 4u && ((h >> 3) & 31) <= 29 && ((h >> 8) & 31) <= 29;  // BFINAL = 0, BTYPE = 10, HLIT / HDIST in range
+            w0 = w1;
+            w1 = __ldg(wp + (rel >> 5) + 2);   // (the input buffer is padded: a word beyond the stream may be read, never used as data)
             const uint32_t m = __ballot_sync(CZK_FULL, ok);
-            if (ok) q[qn + __popc(m & ((1u << lane) - 1u))] = (uint32_t)(b - ch.lo_bit);
+            if (ok) q[qn + __popc(m & ((1u << lane) - 1u))] = r;
             qn += __popc(m);
             __syncwarp();
         }
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(128) inflate_candidates_kernel(const uint8_t *
             uint32_t hlit = 0, hdist = 0, hclen = 0;
             uint64_t clbits = 0;
             if (ok) {
-                b = ch.lo_bit + q[lane];
+                b = (word0 << 5) + q[lane];
                 const uint32_t h = cand_bits(words, b, 17);
                 hlit = (h >> 3) & 31; hdist = (h >> 8) & 31; hclen = ((h >> 13) & 15) + 4;
                 clbits = cand_bits64(words, b + 17) & ((1ull << (3 * hclen)) - 1ull);  // 3 * hclen <= 57
@@ -180,7 +190,7 @@ __global__ void __launch_bounds__(128) inflate_candidates_kernel(const uint8_t *
             }
             if (ok) ok = cand_full_check(words, b, ch.end_bit, hlit, hdist, hclen, clbits);
             const uint32_t m = __ballot_sync(CZK_FULL, ok);
-            if (m) { found = ch.lo_bit + q[__ffs((int)m) - 1]; break; }  // (the queue is ascending: the lowest lane is the first offset)
+            if (m) { found = (word0 << 5) + q[__ffs((int)m) - 1]; break; }  // (the queue is ascending: the lowest lane is the first offset)
             __syncwarp();
             const uint32_t rest = qn - take;  // < 32
             const uint32_t moved = lane < rest ? q[take + lane] : 0u;

@@ -236,8 +236,8 @@ int inflate_runs_batch(BK &bk, std::vector<BigUnit> &units, uint64_t chunk_bytes
             if (!ok) { dead[u] = 1; continue; }
             R.swap(keep);
         }
+        bk.mark("decode round");
     }
-    bk.mark("decode rounds");
     // ---- 4. layout of the units whose chain closed
     struct LRun { uint32_t unit; uint64_t start, target; uint32_t mid; uint64_t out_len; uint32_t first, ntok; int32_t status; uint64_t tok_off, tok_cap, end; };
     std::vector<LRun> L;
