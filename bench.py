@@ -80,9 +80,10 @@ def load_peaks():
 
 
 def kernel_source_hash():
-    """Identifies the kernel sources a profile belongs to: sha256 over compu_b200/csrc/*.cu, *.cuh, *.h (sorted)."""
+    """Identifies the kernel sources a profile belongs to: sha256 over compu_b200/csrc/*.cuh (sorted) — every __global__
+    function of the library lives in a .cuh; the .cu / .h files are the host side of the ABI."""
     h = hashlib.sha256()
-    for f in sorted(glob.glob(os.path.join(ROOT, "compu_b200", "csrc", "*.cu*")) + glob.glob(os.path.join(ROOT, "compu_b200", "csrc", "*.h"))):
+    for f in sorted(glob.glob(os.path.join(ROOT, "compu_b200", "csrc", "*.cuh"))):
         h.update(os.path.basename(f).encode())
         h.update(open(f, "rb").read())
     return h.hexdigest()[:16]

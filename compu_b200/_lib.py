@@ -26,6 +26,7 @@ SIGNATURES = {
     "cz_launch_count": (u64, []),
     "cz_host_alloc": (vp, [sz]),
     "cz_host_free": (None, [vp]),
+    "cz_set_stream_device": (ci, [ci]),
     "cz_decoder_new": (vp, [ci]),
     "cz_decode": (CzResult, [vp, vp, sz, vp, sz]),
     "cz_decoder_reset": (vp, [vp]),

@@ -924,6 +924,7 @@ struct EncoderState {
     uint32_t adler = 1, crc = 0;
     uint64_t total_in = 0;
     int last_rank = -4;    // zlib's RANK(last_flush); deflateReset leaves last_flush = -2
+    int dev = 0;           // the device this encoder compresses on (cz_set_stream_device at construction)
 };
 
 extern "C" void *cz_encoder_new(int level, int window_bits, int mem_level, int strategy) {
@@ -938,6 +939,7 @@ extern "C" void *cz_encoder_new(int level, int window_bits, int mem_level, int s
     EncoderState *s = new (std::nothrow) EncoderState();
     if (!s) return nullptr;
     s->level = level; s->window_bits = window_bits; s->mem_level = mem_level; s->strategy = strategy;
+    s->dev = stream_device();
     return s;
 }
 
@@ -976,7 +978,7 @@ static int encoder_emit(EncoderState *s, size_t nbytes, bool empty_marker, bool 
         J.in = s->in.as<uint8_t>(); J.unit_off = off; J.n = 1; J.seg_bytes = S; J.level = s->level; J.strategy = s->strategy;
         J.check_kind = s->window_bits == 15 ? 1 : s->window_bits > 15 ? 2 : 0;
         J.dst.assign(1, o + k); J.dst_cap.assign(1, need - k);
-        int rc = deflate_engine(J, 1);
+        int rc = deflate_engine(J, 1u << s->dev);
         if (rc) return rc;
         if (J.res[0].status != CZ_ENCODE_FINISHED) { set_error("internal: staged output bound too small"); return CZ_E_MEM; }
         k += J.res[0].payload_len;

@@ -578,12 +578,24 @@ struct DecoderState {
     }
 };
 
+static std::atomic<int> g_stream_device{0};
+namespace czh { int stream_device() { return g_stream_device.load(std::memory_order_relaxed); } }
+
+extern "C" int cz_set_stream_device(int device) {
+    if (probe_devices() == 0 || !device_ctx(device)) {
+        if (!g_err[0]) set_error("no usable sm_100 CUDA device %d", device);
+        return CZ_E_NO_DEVICE;
+    }
+    g_stream_device.store(device, std::memory_order_relaxed);
+    return 0;
+}
+
 extern "C" void *cz_decoder_new(int window_bits) {
     if (!(window_bits == -15 || window_bits == 15 || window_bits == 31 || window_bits == 47)) {
         set_error("unsupported window_bits %d", window_bits);
         return nullptr;
     }
-    int dev = 0;
+    const int dev = stream_device();
     if (probe_devices() == 0 || !device_ctx(dev)) {
         if (!g_err[0]) set_error("no usable sm_100 CUDA device");
         return nullptr;  // => Interface::zlib_cuda(mode) returns None; there is no CPU path

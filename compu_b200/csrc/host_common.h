@@ -29,6 +29,7 @@ struct DeviceCtx {
 };
 DeviceCtx *device_ctx(int dev);  // nullptr if the device is unusable (not sm_100, CUDA failure)
 int usable_device_count();
+int stream_device();  // the device new streaming Decoder / Encoder objects are placed on (cz_set_stream_device, default 0)
 
 // Grow-only device / pinned-host buffers reused across calls (reset() keeps the allocation).
 struct DevBuf {

@@ -81,6 +81,12 @@ void cz_host_free(void *p);
 
 /* ---------------------------------------------------------------- streaming decoder ---------------- */
 
+/* The device on which cz_decoder_new / cz_encoder_new place the objects they create from now on (process-wide, default 0; an
+ * object stays on the device it was created on). compu has no counterpart: its backends run where the caller's thread runs
+ * (the rayon baseline creates one handle per worker, src/decoder/mod.rs:196-204); a worker bound to GPU k calls this once.
+ * Returns 0, or CZ_E_NO_DEVICE. */
+int cz_set_stream_device(int device);
+
 void *cz_decoder_new(int window_bits); /* NULL on failure => Interface::zlib_cuda returns None */
 cz_result cz_decode(void *state, const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len);
 void *cz_decoder_reset(void *state); /* instance to use from now on; NULL = failed */

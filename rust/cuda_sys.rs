@@ -29,6 +29,7 @@ extern "C" {
     pub fn cz_host_alloc(bytes: usize) -> *mut c_void;
     pub fn cz_host_free(p: *mut c_void);
 
+    pub fn cz_set_stream_device(device: c_int) -> c_int;
     pub fn cz_decoder_new(window_bits: c_int) -> *mut c_void;
     pub fn cz_decode(state: *mut c_void, input: *const u8, in_len: usize, output: *mut u8, out_len: usize) -> cz_result;
     pub fn cz_decoder_reset(state: *mut c_void) -> *mut c_void;

@@ -138,3 +138,12 @@ def test_eight_threads_with_their_own_handles(alice):
     for t in th:
         t.join()
     assert not errors, errors
+
+
+def test_stream_device_selection_rejects_missing_devices():
+    from compu_b200 import _lib
+    L = _lib.lib()
+    assert L.cz_set_stream_device(0) == 0
+    assert L.cz_set_stream_device(63) != 0 and L.cz_set_stream_device(-1) != 0   # CZ_E_NO_DEVICE, the selection stays
+    d = dec.Interface.zlib_cuda(dec.ZlibMode.Zlib)
+    assert d is not None

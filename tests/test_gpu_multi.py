@@ -46,3 +46,26 @@ def test_deflate_two_devices_identical_bytes(alice):
     a, st = batch.deflate_batch(bufs, level=6, window_bits=15, devices_mask=mask)
     b, st1 = batch.deflate_batch(bufs, level=6, window_bits=15, devices_mask=1)
     assert a == b and (st == 2).all()
+
+
+@pytest.mark.skipif("_ndev() < 2")
+def test_streaming_objects_on_the_second_device(alice):
+    """cz_set_stream_device places new Decoder / Encoder objects on another GPU; bytes and statuses do not depend on it."""
+    from compu_b200 import Vec
+    from compu_b200 import decoder as dec
+    from compu_b200 import encoder as enc
+    L = _lib.lib()
+    data = alice * 3
+    opts = lambda: enc.ZlibOptions().mode(enc.ZlibMode.Zlib).compression(6)
+    try:
+        assert L.cz_set_stream_device(1) == 0
+        e = enc.Interface.zlib_cuda(opts())
+        d = dec.Interface.zlib_cuda(dec.ZlibMode.Zlib)
+    finally:
+        assert L.cz_set_stream_device(0) == 0   # (objects stay where they were created)
+    cv, cv0, pv = Vec(), Vec(), Vec()
+    assert e.encode_vec_full(data, cv, enc.EncodeOp.Finish).status == enc.EncodeStatus.Finished
+    enc.Interface.zlib_cuda(opts()).encode_vec_full(data, cv0, enc.EncodeOp.Finish)
+    assert cv.as_bytes() == cv0.as_bytes() and zlib.decompress(cv.as_bytes()) == data
+    assert d.decode_vec_full(cv.as_bytes(), pv).status == dec.DecodeStatus.Finished
+    assert pv.as_bytes() == data

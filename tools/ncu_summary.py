@@ -30,6 +30,7 @@ CURATED = [
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
     "smsp__cycles_active.avg", "sm__cycles_elapsed.max",
 ]
 
