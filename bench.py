@@ -99,7 +99,8 @@ def traffic_entry(key):
         return None, "profiles/traffic.json missing"
     if t.get("src_hash") != kernel_source_hash():
         return None, "profiles/traffic.json was captured on other kernel sources (src_hash %s != %s)" % (t.get("src_hash"), kernel_source_hash())
-    return t.get(key), t.get("source", "profiles/traffic.json")
+    src_key = {"deflate_cfg3_dram_bytes_per_launch": "deflate_cfg3_source"}.get(key, "source")
+    return t.get(key), t.get(src_key, "profiles/traffic.json")
 
 
 def cpu_threads():
