@@ -59,43 +59,42 @@ __host__ __device__ inline uint32_t cand_kraft9(uint32_t x) {
     return k;
 }
 
-// Full check of a dynamic block header at absolute bit `b`: the cheap filters have passed and the code-length code (its hclen
-// 3-bit lengths are the low bits of `clbits`, in transmission order) is complete. Lane-serial, rare.
-__device__ inline bool cand_full_check(const uint32_t *words, uint64_t b, uint64_t end_bit, uint32_t hlit, uint32_t hdist, uint32_t hclen,
-                                       uint64_t clbits) {
-    uint64_t pos = b + 17 + 3ull * hclen;
-    const uint64_t order_lo = 16ull | (17ull << 5) | (18ull << 10) | (0ull << 15) | (8ull << 20) | (7ull << 25) |
-                              (9ull << 30) | (6ull << 35) | (10ull << 40) | (5ull << 45) | (11ull << 50) | (4ull << 55);
-    const uint64_t order_hi = 12ull | (3ull << 5) | (13ull << 10) | (2ull << 15) | (14ull << 20) | (1ull << 25) | (15ull << 30);
-    uint64_t cl_lens = 0;  // 19 x 3 bits, indexed by symbol
-    for (uint32_t i = 0; i < hclen; i++) {
-        const uint32_t l = (uint32_t)(clbits >> (3 * i)) & 7;
-        const uint32_t sym = i < 12 ? (uint32_t)(order_lo >> (5 * i)) & 31 : (uint32_t)(order_hi >> (5 * (i - 12))) & 31;
-        cl_lens |= (uint64_t)l << (3 * sym);
+// The decode table of a COMPLETE code-length code, built by the whole warp into tab[128] (entry = symbol << 3 | length, indexed
+// by the next 7 input bits): lane s < 19 owns symbol s — its length comes from the header's 3-bit fields (`clbits`, transmission
+// order), the per-length counts from ballots, its canonical code from its rank among the symbols of its length — and fills the
+// 2^(7 - length) entries of its code. (The survivors of the second filter are rare, so one lane used to build this alone: ~650
+// of the ~950 instructions of a full check, profiles/r2_runs_gzip_cfg4_ncu.md.)
+__device__ __forceinline__ void cand_build_cl_tab_warp(uint8_t *tab, uint64_t clbits, uint32_t hclen, uint32_t lane) {
+    // transmission index of symbol s (inverse of 16 17 18 0 8 7 9 6 10 5 11 4 12 3 13 2 14 1 15), 5 bits per symbol
+    const uint64_t inv_lo = 3ull | (17ull << 5) | (15ull << 10) | (13ull << 15) | (11ull << 20) | (9ull << 25) | (7ull << 30) |
+                            (5ull << 35) | (4ull << 40) | (6ull << 45) | (8ull << 50) | (10ull << 55);      // symbols 0..11
+    const uint64_t inv_hi = 12ull | (14ull << 5) | (16ull << 10) | (18ull << 15) | (0ull << 20) | (1ull << 25) | (2ull << 30);  // 12..18
+    uint32_t l = 0;
+    if (lane < 19) {
+        const uint32_t idx = lane < 12 ? (uint32_t)(inv_lo >> (5 * lane)) & 31 : (uint32_t)(inv_hi >> (5 * (lane - 12))) & 31;
+        if (idx < hclen) l = (uint32_t)(clbits >> (3 * idx)) & 7;
     }
-    // canonical codes of the (complete) code-length code: symbols per length and first code per length, packed
-    uint64_t cntp = 0;  // 5 bits per length
-    for (uint32_t s = 0; s < 19; s++) {
-        const uint32_t l = (uint32_t)(cl_lens >> (3 * s)) & 7;
-        if (l) cntp += 1ull << (5 * l);
-    }
-    uint64_t nextp = 0;  // 8 bits per length
-    uint32_t code = 0;
+    uint32_t code = 0, my_code = 0;
+#pragma unroll
     for (uint32_t len = 1; len <= 7; len++) {
-        const uint32_t c = (uint32_t)(cntp >> (5 * len)) & 31;
-        nextp |= (uint64_t)code << (8 * len);
-        code = (code + c) << 1;
+        const uint32_t m = __ballot_sync(CZK_FULL, l == len);
+        if (l == len) my_code = code + __popc(m & ((1u << lane) - 1u));
+        code = (code + __popc(m)) << 1;
     }
-    uint8_t cl_tab[128];  // symbol << 3 | length (a complete code fills every entry)
-    for (uint32_t s = 0; s < 19; s++) {
-        const uint32_t l = (uint32_t)(cl_lens >> (3 * s)) & 7;
-        if (!l) continue;
-        const uint32_t c = (uint32_t)(nextp >> (8 * l)) & 0xff;
-        nextp += 1ull << (8 * l);
-        const uint32_t rev = __brev(c) >> (32 - l);
-        for (uint32_t idx = rev; idx < 128; idx += (1u << l)) cl_tab[idx] = (uint8_t)((s << 3) | l);
+    if (l) {
+        const uint32_t rev = __brev(my_code) >> (32 - l);
+        const uint8_t e = (uint8_t)((lane << 3) | l);
+        for (uint32_t idx = rev; idx < 128; idx += (1u << l)) tab[idx] = e;
     }
-    // the code lengths themselves: Kraft sums of both alphabets on the fly, so random bits fail after a few symbols
+    __syncwarp();
+}
+
+// Full check of a dynamic block header at absolute bit `b`: the cheap filters have passed, the code-length code is complete and
+// its table is in cl_tab. Decodes the code lengths with the Kraft sums of both alphabets on the fly, so random bits fail after a
+// few symbols. Lane-serial, rare.
+__device__ __forceinline__ bool cand_full_check(const uint32_t *words, const uint8_t *cl_tab, uint64_t b, uint64_t end_bit, uint32_t hlit, uint32_t hdist,
+                                       uint32_t hclen) {
+    uint64_t pos = b + 17 + 3ull * hclen;
     const uint32_t nlit = hlit + 257, total = nlit + hdist + 1;
     uint32_t i = 0, prev = 0, lit_sum = 0, dist_sum = 0, eob_len = 0, dist_codes = 0;
     while (i < total) {
@@ -129,13 +128,57 @@ __device__ inline bool cand_full_check(const uint32_t *words, uint64_t b, uint64
     return true;
 }
 
+// Examines the first min(32, qn) queued offsets (ascending, relative to bit0) with the second and third filter; returns the
+// absolute bit of the first one that is a valid header (the rest of the queue no longer matters then), or ~0 after having
+// removed them from the queue. Called by the whole warp.
+__device__ __forceinline__ uint64_t cand_examine(const uint32_t *words, uint64_t bit0, uint64_t end_bit, uint32_t *q, uint32_t &qn,
+                                                 const uint8_t *kraft9, uint8_t *cl_tab, uint32_t lane) {
+    const uint32_t take = qn < 32 ? qn : 32;
+    bool ok = lane < take;
+    uint64_t b = 0;
+    uint32_t hlit = 0, hdist = 0, hclen = 0;
+    uint64_t clbits = 0;
+    if (ok) {
+        b = bit0 + q[lane];
+        const uint32_t h = cand_bits(words, b, 17);
+        hlit = (h >> 3) & 31; hdist = (h >> 8) & 31; hclen = ((h >> 13) & 15) + 4;
+        clbits = cand_bits64(words, b + 17) & ((1ull << (3 * hclen)) - 1ull);  // 3 * hclen <= 57
+        uint32_t k = 0;
+#pragma unroll
+        for (int f = 0; f < 7; f++) k += kraft9[(uint32_t)(clbits >> (9 * f)) & 511u];
+        ok = k == 128u;  // zlib: an incomplete (or over-subscribed) code-length code is always an error
+    }
+    // the rare survivors, one after the other: the warp builds the table, the survivor's lane decodes the code lengths
+    for (uint32_t pend = __ballot_sync(CZK_FULL, ok); pend; pend &= pend - 1) {
+        const int src = __ffs((int)pend) - 1;
+        cand_build_cl_tab_warp(cl_tab, __shfl_sync(CZK_FULL, clbits, src), __shfl_sync(CZK_FULL, hclen, src), lane);
+        if ((int)lane == src) ok = cand_full_check(words, cl_tab, b, end_bit, hlit, hdist, hclen);
+        __syncwarp();
+    }
+    const uint32_t m = __ballot_sync(CZK_FULL, ok);
+    if (m) return bit0 + q[__ffs((int)m) - 1];  // (the queue is ascending: the lowest lane is the first offset)
+    __syncwarp();
+    const uint32_t rest = qn - take;  // < 32
+    const uint32_t moved = lane < rest ? q[take + lane] : 0u;
+    __syncwarp();
+    if (lane < rest) q[lane] = moved;
+    qn = rest;
+    __syncwarp();
+    return ~0ull;
+}
+
 // cand[c] = absolute bit of the first plausible dynamic block header in chunk c, or ~0. Three filters of rising cost per bit
 // offset: the 17 header bits (BFINAL = 0, BTYPE = 10, HLIT / HDIST in range: ~11 % of random offsets pass); the Kraft sum of
 // the code-length code from a table over 9 bits (three lengths) at a time — it must be complete, which ~0.5 % of those are;
 // then the full decode of the code lengths.
+// Only ~11 % of the offsets pass the first filter, but with 32 offsets per step some lane nearly always does, and the warp would
+// pay for the second filter at every step: the survivors are queued instead and examined 32 at a time, all lanes busy. The scan
+// itself runs on 32-bit offsets relative to the word that holds the chunk's first bit, one (warp-uniform) word load per step:
+// lane l examines the 17 bits at bit l of the 64-bit window [w0, w1].
 __global__ void __launch_bounds__(128) inflate_candidates_kernel(const uint8_t *in, const CandChunk *chunks, uint32_t n_chunks, uint64_t *cand) {
     __shared__ uint8_t kraft9[512];
-    __shared__ uint32_t queue[4][64];  // per warp: offsets (relative to the chunk's first bit) that passed the 17-bit filter, ascending
+    __shared__ uint8_t cl_tabs[4][128];  // per warp: the code-length decode table of the header under the full check
+    __shared__ uint32_t queue[4][64];    // per warp: offsets that passed the 17-bit filter, ascending
     for (uint32_t i = threadIdx.x; i < 512; i += blockDim.x) kraft9[i] = (uint8_t)cand_kraft9(i);
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -144,63 +187,35 @@ __global__ void __launch_bounds__(128) inflate_candidates_kernel(const uint8_t *
     const CandChunk ch = chunks[c];
     const uint32_t *words = (const uint32_t *)in;  // `in` is the (256-byte aligned) base of the device input buffer
     uint32_t *q = queue[warp];
-    uint64_t found = ~0ull;
-    uint32_t qn = 0;
-    // Only ~11 % of the offsets pass the first filter, but with 32 offsets per step some lane nearly always does, and the warp paid
-    // for the second filter at every step. The survivors are queued instead and examined 32 at a time, all lanes busy.
-    // The scan itself runs on 32-bit offsets relative to the word that holds the chunk's first bit, one (warp-uniform) word load
-    // per step: lane l examines the 17 bits at bit l of the 64-bit window [w0, w1].
     const uint64_t word0 = ch.lo_bit >> 5;                                   // first word of the scan
+    const uint64_t bit0 = word0 << 5;
     const uint32_t first = (uint32_t)(ch.lo_bit & 31);                       // offsets below this lie before the chunk
     uint64_t last64 = ch.hi_bit;                                             // offsets >= last are out: end of the chunk, or too
     if (ch.end_bit < 17 + 57 + 14) last64 = 0;                               // close to the end of the stream for a header
     else if (ch.end_bit - (17 + 57 + 14) + 1 < last64) last64 = ch.end_bit - (17 + 57 + 14) + 1;
-    const uint32_t last = last64 > (word0 << 5) ? (uint32_t)(last64 - (word0 << 5)) : 0u;   // (a chunk is far below 2^32 bits)
-    const uint32_t span = (uint32_t)(ch.hi_bit - (word0 << 5));
+    const uint32_t last = last64 > bit0 ? (uint32_t)(last64 - bit0) : 0u;    // (a chunk is far below 2^32 bits)
+    const uint32_t span = (uint32_t)(ch.hi_bit - bit0);
     const uint32_t *wp = words + word0;
     uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1);
-    for (uint32_t rel = 0; found == ~0ull; rel += 32) {
-        const bool more = rel < span;
-        if (more) {
-            const uint32_t r = rel + lane;
-            const uint32_t h = __funnelshift_r(w0, w1, lane) & 0x1ffffu;
-            const bool ok = r >= first && r < last && (h & 7u) == 4u && ((h >> 3) & 31) <= 29 && ((h >> 8) & 31) <= 29;  // BFINAL = 0, BTYPE = 10, HLIT / HDIST in range
-            w0 = w1;
-            w1 = __ldg(wp + (rel >> 5) + 2);   // (the input buffer is padded: a word beyond the stream may be read, never used as data)
-            const uint32_t m = __ballot_sync(CZK_FULL, ok);
-            if (ok) q[qn + __popc(m & ((1u << lane) - 1u))] = r;
-            qn += __popc(m);
-            __syncwarp();
+    uint64_t found = ~0ull;
+    uint32_t qn = 0;
+    for (uint32_t rel = 0; rel < span; rel += 32) {
+        const uint32_t r = rel + lane;
+        const uint32_t h = __funnelshift_r(w0, w1, lane) & 0x1ffffu;
+        const bool ok = r >= first && r < last && (h & 7u) == 4u && ((h >> 3) & 31) <= 29 && ((h >> 8) & 31) <= 29;  // BFINAL = 0, BTYPE = 10, HLIT / HDIST in range
+        w0 = w1;
+        wp++;
+        w1 = __ldg(wp + 1);   // (the input buffer is padded: a word beyond the stream may be read, never used as data)
+        const uint32_t m = __ballot_sync(CZK_FULL, ok);
+        if (ok) q[qn + __popc(m & ((1u << lane) - 1u))] = r;
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
+            found = cand_examine(words, bit0, ch.end_bit, q, qn, kraft9, cl_tabs[warp], lane);
+            if (found != ~0ull) break;
         }
-        while (qn >= 32 || (!more && qn)) {
-            const uint32_t take = qn < 32 ? qn : 32;
-            bool ok = lane < take;
-            uint64_t b = 0;
-            uint32_t hlit = 0, hdist = 0, hclen = 0;
-            uint64_t clbits = 0;
-            if (ok) {
-                b = (word0 << 5) + q[lane];
-                const uint32_t h = cand_bits(words, b, 17);
-                hlit = (h >> 3) & 31; hdist = (h >> 8) & 31; hclen = ((h >> 13) & 15) + 4;
-                clbits = cand_bits64(words, b + 17) & ((1ull << (3 * hclen)) - 1ull);  // 3 * hclen <= 57
-                uint32_t k = 0;
-#pragma unroll
-                for (int f = 0; f < 7; f++) k += kraft9[(uint32_t)(clbits >> (9 * f)) & 511u];
-                ok = k == 128u;  // zlib: an incomplete (or over-subscribed) code-length code is always an error
-            }
-            if (ok) ok = cand_full_check(words, b, ch.end_bit, hlit, hdist, hclen, clbits);
-            const uint32_t m = __ballot_sync(CZK_FULL, ok);
-            if (m) { found = (word0 << 5) + q[__ffs((int)m) - 1]; break; }  // (the queue is ascending: the lowest lane is the first offset)
-            __syncwarp();
-            const uint32_t rest = qn - take;  // < 32
-            const uint32_t moved = lane < rest ? q[take + lane] : 0u;
-            __syncwarp();
-            if (lane < rest) q[lane] = moved;
-            qn = rest;
-            __syncwarp();
-        }
-        if (!more) break;
     }
+    while (found == ~0ull && qn) found = cand_examine(words, bit0, ch.end_bit, q, qn, kraft9, cl_tabs[warp], lane);
     if (lane == 0) cand[c] = found;
 }
 
