@@ -334,7 +334,7 @@ uint64_t runs_min_unit_bytes() { return std::max<uint64_t>(64u << 10, 4 * runs_c
 // Decodes the long streams `ids` of a packed host batch on device `dev` with the block-parallel path, in batches bounded by
 // device memory. done[i] = 1 for the units it decoded (out, out_lens, statuses = Finished, in_consumed written); the others
 // are left untouched for the serial path.
-static DevicePool<CudaRunsBackend, 2> g_runs_pool;
+static DevicePool<CudaRunsBackend, 4> g_runs_pool;
 
 // One batch [a, b) of `ids` on backend `bk`: host -> device, the run pipeline, device -> host, results.
 static int inflate_long_batch(CudaRunsBackend *bk, const std::vector<size_t> &ids, size_t a, size_t b, const uint8_t *in,
@@ -402,7 +402,8 @@ int inflate_long_units(int dev, const std::vector<size_t> &ids, const uint8_t *i
     uint64_t total_in = 0;
     for (size_t i : ids) total_in += in_off[i + 1] - in_off[i];
     const bool small_job = total_in <= (768ull << 20);
-    const uint64_t batch_in = small_job ? (1024ull << 20) : (384ull << 20), batch_out = small_job ? (2048ull << 20) : (1024ull << 20);
+    static const uint64_t batch_mb = [] { const char *e = getenv("CZ_RUNS_BATCH_MB"); long v = e ? atol(e) : 0; return v >= 16 && v <= 4096 ? (uint64_t)v : 384ull; }();
+    const uint64_t batch_in = small_job ? (1024ull << 20) : (batch_mb << 20), batch_out = small_job ? (2048ull << 20) : ((batch_mb * 8 / 3) << 20);
     std::vector<size_t> cut(1, 0);
     {
         size_t a = 0;
@@ -421,22 +422,35 @@ int inflate_long_units(int dev, const std::vector<size_t> &ids, const uint8_t *i
         }
     }
     const size_t nb = cut.size() - 1;
-    const int nworkers = nb > 1 ? 2 : 1;
+    // every backend is sized for the largest batch of the call up front: which backend gets which batch depends on timing, and a
+    // buffer that has to grow in the middle of the call costs a cudaFree + cudaMalloc (a device-wide synchronisation)
+    uint64_t max_in = 0, max_span = 0;
+    for (size_t k = 0; k < nb; k++) {
+        uint64_t ib = 0;
+        for (size_t q = cut[k]; q < cut[k + 1]; q++) ib += runs_align(in_off[ids[q] + 1] - in_off[ids[q]] + 64);
+        max_in = std::max(max_in, ib);
+        max_span = std::max(max_span, out_off[ids[cut[k + 1] - 1] + 1] - out_off[ids[cut[k]]]);
+    }
+    // (2 / 3 / 4 backends measured on the cfg5 shape, 3 batches on one GPU: see profiles/r2_notes.md)
+    static const int max_workers = [] { const char *e = getenv("CZ_RUNS_WORKERS"); int v = e ? atoi(e) : 0; return v >= 1 && v <= 4 ? v : 3; }();
+    const int nworkers = (int)std::min<size_t>(nb, (size_t)max_workers);
     std::vector<int> rcs(nworkers, 0);
     auto worker = [&](int w) {
         if (!CZ_CUDA(cudaSetDevice(dev))) { rcs[w] = CZ_E_MEM; return; }
         CudaRunsBackend *bk = g_runs_pool.acquire(dev);
         if (!bk) { rcs[w] = CZ_E_MEM; return; }
         if (!bk->init(ctx)) rcs[w] = CZ_E_MEM;
+        if (nb > 1 && !(bk->in.reserve(max_in + 256) && bk->out.reserve(max_span + 256) && bk->tokbuf.reserve(10 * max_in + (8u << 20))))
+            cudaGetLastError();  // (not fatal: the batches reserve what they need themselves)
         for (size_t k = (size_t)w; k < nb && !rcs[w]; k += (size_t)nworkers)
             rcs[w] = inflate_long_batch(bk, ids, cut[k], cut[k + 1], in, in_off, out, out_off, out_lens, statuses, in_consumed, window_bits, done);
         g_runs_pool.release(dev, bk);
     };
-    if (nworkers == 1) worker(0);
-    else {
-        std::thread t(worker, 1);
+    {
+        std::vector<std::thread> th;
+        for (int w = 1; w < nworkers; w++) th.emplace_back(worker, w);
         worker(0);
-        t.join();
+        for (auto &t : th) t.join();
     }
     for (int r : rcs) if (r) return r;
     return 0;
