@@ -498,12 +498,6 @@ static int slot_back(DeflateSlot &w, EngineJob &J) {
     const uint64_t total = *(const uint64_t *)(hr + w.res_off_total);
     if (J.seg_sizes) memcpy(J.seg_sizes->data() + w.s0, hr + w.res_off_segsz, 8 * (w.s1 - w.s0));
     cudaStream_t st = w.stream;
-    const bool direct = np <= 16;
-    if (!direct) {
-        if (!w.stage.reserve(total + 64)) return CZ_E_MEM;
-        if (total && !CZ_CUDA(cudaMemcpyAsync(w.stage.p, w.out.p, total, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
-        if (!CZ_CUDA(cudaStreamSynchronize(st))) return CZ_E_MEM;
-    }
     // destinations (sequential: pieces of one unit arrive in order)
     std::vector<uint8_t *> dst(np, nullptr);
     for (size_t p = 0; p < np; p++) {
@@ -518,16 +512,39 @@ static int slot_back(DeflateSlot &w, EngineJob &J) {
         J.unit_written[u] += lens[p];
         R.payload_len = J.unit_written[u];
     }
-    if (direct) {
-        for (size_t p = 0; p < np; p++)
+    // Payloads leave the device packed. A large piece is copied straight into the caller's buffer by the copy engine (no staging
+    // of ours when that buffer is pinned); consecutive small pieces — one copy each would cost more in launches than in bytes —
+    // leave in one copy to pinned staging and are placed by the host.
+    const uint64_t kDirect = 128u << 10;
+    const bool few = np <= 16;
+    std::vector<uint32_t> staged;  // pieces that leave through the staging buffer
+    uint64_t staged_bytes = 0;
+    if (!few) {
+        if (!w.stage.reserve(total + 64)) return CZ_E_MEM;
+    }
+    for (size_t p = 0; p < np;) {
+        if (few || lens[p] >= kDirect) {
             if (dst[p] && lens[p] && !CZ_CUDA(cudaMemcpyAsync(dst[p], w.out.as<uint8_t>() + pos[p], lens[p], cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
-        if (!CZ_CUDA(cudaStreamSynchronize(st))) return CZ_E_MEM;
-        CZ_TRACE_PT("back payload copied", w.b);
-    } else {
+            p++;
+            continue;
+        }
+        size_t e = p;
+        while (e < np && lens[e] < kDirect && (e == p || pos[e] == pos[e - 1] + lens[e - 1])) e++;
+        const uint64_t a = pos[p], b = pos[e - 1] + lens[e - 1];
+        if (b > a && !CZ_CUDA(cudaMemcpyAsync(w.stage.as<uint8_t>() + a, w.out.as<uint8_t>() + a, b - a, cudaMemcpyDeviceToHost, st))) return CZ_E_MEM;
+        for (size_t q = p; q < e; q++) staged.push_back((uint32_t)q);
+        staged_bytes += b - a;
+        p = e;
+    }
+    if (!CZ_CUDA(cudaStreamSynchronize(st))) return CZ_E_MEM;
+    CZ_TRACE_PT("back payload copied", w.b);
+    if (!staged.empty()) {
         const uint8_t *sp = w.stage.as<uint8_t>();
-#pragma omp parallel for schedule(static) if (total > (1u << 20))
-        for (long p = 0; p < (long)np; p++)
+#pragma omp parallel for schedule(static) if (staged_bytes > (1u << 20))
+        for (long k = 0; k < (long)staged.size(); k++) {
+            const size_t p = staged[k];
             if (dst[p]) memcpy(dst[p], sp + pos[p], lens[p]);
+        }
     }
     return 0;
 }
