@@ -107,9 +107,6 @@ __device__ __forceinline__ uint32_t czk_ldg_stream(const uint32_t *p) {
 #ifndef CZK_LZ_WIDE
 #define CZK_LZ_WIDE 1  // phase B: short matches read their source as aligned 8-byte words (0: one load per byte)
 #endif
-#ifndef CZK_LZ_PF
-#define CZK_LZ_PF 0  // phase B look-ahead: 0 off, 1 prefetch the next group's sources into L2, 2 into L1
-#endif
 #ifndef CZK_LZ_SHORT
 #define CZK_LZ_SHORT 12
 #endif
@@ -524,31 +521,10 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_L
         uint64_t opos = 0, ck_pos = 0;
         uint32_t adler = 1, crc = 0;
         uint32_t ti = 0;
-#if CZK_LZ_PF
-        // Look-ahead (H == 0): the tokens of the next two groups travel in registers, and while group g is resolved the far
-        // back-references of group g+1 are prefetched — the warp used to wait twice per group for a DRAM / L2 round trip
-        // (token load, then the sources; the windows of the streams in flight exceed L2), now both are requested one group early.
-        uint32_t tA = 0, tB = 0;
-        bool la_ok = false;
-#endif
         while (ti < ntok) {
-#if CZK_LZ_PF
-            uint32_t t_raw;
-            if (la_ok) { t_raw = tA; tA = tB; }
-            else {
-                t_raw = ti + lane < ntok ? tok[ti + lane] : CZK_TOK_STORED;
-                tA = ti + 32 + lane < ntok ? tok[ti + 32 + lane] : CZK_TOK_STORED;
-            }
-            tB = ti + 64 + lane < ntok ? tok[ti + 64 + lane] : CZK_TOK_STORED;
-            la_ok = true;
-#else
             const uint32_t t_raw = ti + lane < ntok ? tok[ti + lane] : CZK_TOK_STORED;  // past the end: acts as a stop mark
-#endif
             const uint32_t stopm = __ballot_sync(CZK_FULL, (t_raw >> 30) == 3u);
             const uint32_t nt = stopm ? (uint32_t)__ffs(stopm) - 1u : 32u;  // ordinary tokens before the first stored mark
-#if CZK_LZ_PF
-            if (nt < 32) la_ok = false;  // the next group does not start 32 words on: load it afresh
-#endif
             if (nt) {
                 const uint32_t t = lane < nt ? t_raw : 0u;
                 const uint32_t tl = (t >> 31) ? ((t >> 24) & 3u) : (t & 0x1ffu);
@@ -561,28 +537,6 @@ __global__ void __launch_bounds__(WARPS * 32, (WARPS * CZK_LZ_MINB <= 32 ? CZK_L
                 }
                 const uint32_t total = __shfl_sync(CZK_FULL, pos, 31);
                 pos -= tl;
-#if CZK_LZ_PF
-                if (H == 0 && nt == 32 && !__any_sync(CZK_FULL, (tA >> 30) == 3u)) {
-                    const uint32_t la_len = (tA >> 31) ? ((tA >> 24) & 3u) : (tA & 0x1ffu);
-                    uint32_t pa = la_len;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        uint32_t v = __shfl_up_sync(CZK_FULL, pa, d);
-                        if ((int)lane >= d) pa += v;
-                    }
-                    pa -= la_len;
-                    if (!(tA >> 31)) {
-                        const uint8_t *src = ob + opos + total + pa - ((tA >> 9) & 0xffffu);
-#if defined(__CUDA_ARCH__) && CZK_LZ_PF == 2
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(src));
-#elif defined(__CUDA_ARCH__)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
-#else
-                        (void)src;
-#endif
-                    }
-                }
-#endif
                 if constexpr (H <= 0) {
                     constexpr int SHORT = H == 0 ? CZK_LZ_SHORT : -H;
                     // ---- token-parallel resolution: lane = token. A token is copied by its own lane (literals; matches of up to
