@@ -109,6 +109,17 @@ static std::mutex g_prof_mu;
 
 static int g_lz_cta = -1, g_lz_spin = -1;
 
+// Launches of phase A with few units (sub-batches of a handful of streams, the runs of one long stream): only every lane_step-th
+// lane of a warp takes a unit. A warp issues every path that any of its lanes takes — literal, length, distance, both refills —
+// so a lane that shares its warp decodes at the pace of all of them together; alone in its warp it is 2-3 x faster. The step is
+// the largest power of two that still fits all units into the lanes resident at 4 warps per CTA, 3 CTAs per SM.
+static uint32_t tok_lane_step(const DeviceCtx *ctx, uint64_t n) {
+    const uint64_t lanes = (uint64_t)ctx->sm_count * 3 * 4 * 32;
+    uint32_t step = 32;
+    while (step > 1 && n * step > lanes) step >>= 1;
+    return step;
+}
+
 template <int WA, int WB, int H>
 static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams &P, void *d_ws, uint64_t ws_bytes,
                             uint64_t total_out_bytes, size_t n_span) {
@@ -177,6 +188,8 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
             if (!CZ_CUDA(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l))) return CZ_E_MEM;
             conf_l[d] = true;
         }
+        // (dense lanes here: these launches are the sub-batches of the pipelined host path, several of them in flight at once —
+        //  one unit per warp made cfg2 end to end 136 ms instead of 98 ms; the sparse launch is for the runs of long streams)
         CZ_KL(kl<<<(unsigned)((P.n + 32 * WL - 1) / (32 * WL)), WL * 32, smem_l, st>>>(Q));
     } else
     CZ_KL(ka<<<(unsigned)ga, WA * 32, smem, st>>>(Q));
@@ -288,8 +301,11 @@ struct CudaRunsBackend {
         const uint32_t n = Q.base.n;
         // few runs: 4 warps per CTA spread over the SMs (a lane decodes sooner when its warp shares the schedulers with 3 others)
         if (n <= (uint32_t)ctx->sm_count * 32 * 4 * 2) {
-            if (Q.count_only) CZ_KL(czk::inflate_tok_kernel<4, false><<<(n + 127) / 128, 128, czk::inflate_tok_smem_bytes<4>(), st>>>(Q));
-            else CZ_KL(czk::inflate_tok_kernel<4, true><<<(n + 127) / 128, 128, czk::inflate_tok_smem_bytes<4>(), st>>>(Q));
+            czk::TwoPhaseParams QL = Q;
+            QL.lane_step = tok_lane_step(ctx, n);
+            const unsigned g = (unsigned)(((uint64_t)n * QL.lane_step + 127) / 128);
+            if (Q.count_only) CZ_KL(czk::inflate_tok_kernel<4, false><<<g, 128, czk::inflate_tok_smem_bytes<4>(), st>>>(QL));
+            else CZ_KL(czk::inflate_tok_kernel<4, true><<<g, 128, czk::inflate_tok_smem_bytes<4>(), st>>>(QL));
         } else {
             uint64_t g = (n + 32 * 14 - 1) / (32 * 14), gmax = (uint64_t)ctx->sm_count * per_sm_tok;
             if (g > gmax) g = gmax;

@@ -71,6 +71,9 @@ struct TwoPhaseParams {
     uint32_t spin_ns;            // inflate_lz_cta_kernel: back-off of a warp that found no ready token
     const RunDesc *runs;         // != null: run mode, one RunDesc per unit
     RunResult *run_res;          // run mode: per unit
+    uint32_t lane_step;          // phase A: > 1 = only lanes with lane % lane_step == 0 take units (launches with few units: a warp
+                                 // pays for every path any of its lanes takes, so a lane that is alone in its warp decodes its
+                                 // stream 2-3 x sooner; the host picks the largest step that still keeps all units in one wave)
 };
 
 __host__ __device__ inline uint64_t tok_word_off(uint64_t out_off, uint64_t unit) { return out_off + 8 * unit; }
@@ -154,6 +157,7 @@ __global__ void __launch_bounds__(WARPS * 32) inflate_tok_kernel(TwoPhaseParams 
 
     for (;;) {
         // ---- (1) fetch work
+        if (st == SS_IDLE && Q.lane_step > 1 && (lane % Q.lane_step) != 0) st = SS_EXIT;
         if (st == SS_IDLE) {
             unsigned long long u = atomicAdd(P.counter, 1ull);
             if (u >= P.n) st = SS_EXIT;

@@ -47,6 +47,7 @@ extern "C" int sim_inflate(size_t n, const uint8_t *in, const uint64_t *in_off, 
             memset(&Q, 0, sizeof Q);
             Q.base = P; Q.tok = tok.data(); Q.meta = meta.data(); Q.counter_b = &counter_b; Q.count_only = 0;
             Q.counter_c = &counter_c; Q.cta_tile = D == -4 ? CZK_LZ_TILE : 0; Q.spin_ns = 0;
+            Q.lane_step = seed % 3 == 0 ? 4 : seed % 3 == 1 ? 32 : 0;  // (the sparse-lane launches of small batches, too)
             cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2>, Q);
             if (D == -4) {
                 cusim::launch(grid, 8 * 32, inflate_lz_cta_smem_bytes<8>(), inflate_lz_cta_kernel<8, 4>, Q);
@@ -123,8 +124,10 @@ struct SimRunsBackend {
     }
     bool tok(const TwoPhaseParams &Q) {
         cusim::set_seed(seed++);
-        if (Q.count_only) cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2, false>, Q);
-        else cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2, true>, Q);
+        TwoPhaseParams QL = Q;
+        QL.lane_step = seed % 3 == 0 ? 8 : seed % 3 == 1 ? 32 : 0;
+        if (Q.count_only) cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2, false>, QL);
+        else cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2, true>, QL);
         return true;
     }
     bool lz16(const TwoPhaseParams &Q, uint16_t *sym) {
