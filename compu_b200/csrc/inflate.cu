@@ -299,6 +299,15 @@ struct CudaRunsBackend {
     }
     bool tok(const czk::TwoPhaseParams &Q) {
         const uint32_t n = Q.base.n;
+        // few runs (one or a few long streams): a warp per run with one decoding lane and look-up tables — up to two waves of
+        // 16 warps per SM; beyond that the lane-per-run kernel's throughput wins
+        static const bool no_warp_runs = getenv("CZ_NO_WARP_RUNS") != nullptr;
+        if (Q.runs && !Q.count_only && !no_warp_runs && n <= (uint32_t)ctx->sm_count * 16 * 2) {
+            unsigned g = (n + 7) / 8, gmax = (unsigned)ctx->sm_count * 2;
+            if (g > gmax) g = gmax;
+            CZ_KL(czk::inflate_tokw_kernel<8><<<g, 256, 0, st>>>(Q));
+            return ok();
+        }
         // few runs: 4 warps per CTA spread over the SMs (a lane decodes sooner when its warp shares the schedulers with 3 others)
         if (n <= (uint32_t)ctx->sm_count * 32 * 4 * 2) {
             czk::TwoPhaseParams QL = Q;

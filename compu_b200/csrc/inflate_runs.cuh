@@ -220,6 +220,194 @@ __global__ void __launch_bounds__(128) inflate_candidates_kernel(const uint8_t *
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// 2b. phase A of a run by a WHOLE WARP with one decoding lane — for launches with few runs (one long stream).
+// In inflate_tok_kernel a warp carries 32 runs and issues every path any of them takes (literal, length, distance, both
+// refills, the canonical code-length searches): a lane decodes at the pace of all 32 together, ~800-1 650 cycles per symbol. Here
+// lane 0 alone decodes ONE run through look-up tables in shared memory (the tables and their warp-cooperative construction are
+// those of inflate_kernel.cuh: 10-bit literal/length, 8-bit distance, canonical search beyond), so only the taken path is issued;
+// the other lanes take part in building the tables. Tokens, TokMeta and RunResult are what inflate_tok_kernel writes in run mode.
+// The clean outcomes are what matters (CZK_ST_RUN_END / ST_FINISHED): the host leaves a stream whose run reports anything else
+// to the serial kernel, which reproduces zlib's partial output and status exactly.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) inflate_tokw_kernel(TwoPhaseParams Q) {
+    const InflateParams &P = Q.base;
+    __shared__ SlotSmem slots[WARPS];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    SlotSmem &my = slots[warp];
+    for (;;) {
+        unsigned long long u64 = 0;
+        if (lane == 0) u64 = atomicAdd(P.counter, 1ull);
+        u64 = __shfl_sync(CZK_FULL, u64, 0);
+        if (u64 >= P.n) break;
+        const uint32_t unit = P.ids ? P.ids[u64] : (uint32_t)u64;
+        const RunDesc rd = Q.runs[unit];
+        const uint8_t *in_base = P.in + rd.in_lo;
+        const uint64_t in_len = rd.in_hi - rd.in_lo;
+        uint32_t *tp = Q.tok + rd.tok_off;
+        uint32_t *const tp0 = tp, *const tp_end = tp + rd.tok_cap;
+        const bool run_mid = rd.mid_stream != 0;
+        BitReader br;
+        br.words = nullptr; br.mis = 0; br.widx = br.wend = 0; br.cnt = 0; br.buf = 0; br.nextw = 0; br.nextw2 = 0; br.total = 0; br.tail_mask = 0xffffffffu;
+        uint64_t pos = 0;
+        uint32_t lit = 0, nlit = 0, bfinal = 0, overflow = 0;
+        int result = 0;
+        bool emit = true;
+#define CZKW_PUT(x) do { if (emit) *tp = (x); tp++; } while (0)
+#define CZKW_FLUSH_LIT() do { if (nlit) { CZKW_PUT(CZK_TOK_LIT | (nlit << 24) | lit); lit = 0; nlit = 0; } } while (0)
+        int st = SS_BLOCK;
+        if (lane == 0) {
+            br.init(in_base, in_len);
+            if (run_mid) {
+                br.seek(rd.start_bit >> 3);
+                br.skip((uint32_t)(rd.start_bit & 7));
+            } else {
+                int wrap;
+                if (P.window_bits < 0) wrap = 0;
+                else if (P.window_bits == 47) { br.refill(); wrap = (in_len >= 2 && br.peek(16) == 0x8b1f) ? 2 : 1; }
+                else wrap = P.window_bits > 15 ? 2 : 1;
+                int r = 0;
+                if (wrap == 1) r = parse_zlib_header(br);
+                else if (wrap == 2) r = parse_gzip_header(br);
+                if (in_len == 0) { result = ST_NEED_OUTPUT; st = SS_FINISH; }
+                else if (r != 0) { result = r == 100 ? ST_NEED_INPUT : r; st = SS_FINISH; }
+            }
+        }
+        // block loop: lane 0 owns the state, the warp follows it
+        for (;;) {
+            uint32_t nl = 0, nd = 0;
+            if (lane == 0 && st == SS_BLOCK) {
+                if (br.consumed() >= rd.target_bit && br.consumed() > rd.start_bit) { result = CZK_ST_RUN_END; st = SS_FINISH; }
+                else {
+                    br.refill();
+                    bfinal = br.get(1);
+                    const uint32_t btype = br.get(2);
+                    if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; }
+                    else if (btype == 0) {
+                        br.skip((uint32_t)((0 - br.consumed()) & 7));
+                        br.refill();
+                        const uint32_t len = br.get(16), nlen = br.get(16);
+                        if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; }
+                        else if ((len ^ 0xffffu) != nlen) { result = ST_E_DATA; st = SS_FINISH; }
+                        else {
+                            const uint64_t ipos = br.consumed() >> 3;
+                            if (ipos + len > in_len) { result = ST_NEED_INPUT; st = SS_FINISH; }
+                            else {
+                                if (emit && tp_end - tp < 16) { emit = false; overflow = 1; }
+                                if (len > 8) {
+                                    CZKW_FLUSH_LIT();
+                                    CZKW_PUT(CZK_TOK_STORED | len);
+                                    CZKW_PUT(CZK_TOK_STORED | CZK_TOK_TAIL | (uint32_t)(ipos & 0x1fffffffu));
+                                    CZKW_PUT(CZK_TOK_STORED | CZK_TOK_TAIL | (uint32_t)(ipos >> 29));
+                                } else {
+                                    for (uint32_t k = 0; k < len; k++) {
+                                        lit |= (uint32_t)in_base[ipos + k] << (8 * nlit);
+                                        if (++nlit == 3) { CZKW_PUT(CZK_TOK_LIT | (3u << 24) | lit); lit = 0; nlit = 0; }
+                                    }
+                                }
+                                pos += len;
+                                br.seek(ipos + len);
+                                if (bfinal) { result = ST_FINISHED; st = SS_FINISH; }
+                            }
+                        }
+                    } else if (btype == 1) {
+                        uint8_t *lens = my.u.lens;
+                        for (uint32_t i = 0; i < 288; i++) lens[i] = (uint8_t)(i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8);
+                        for (uint32_t i = 0; i < 32; i++) lens[288 + i] = 5;
+                        nl = 288; nd = 32;
+                        st = SS_BUILD;
+                    } else if (btype == 2) {
+                        int r = parse_dynamic_header(br, my, nl, nd);
+                        if (r == ST_E_DATA && br.consumed() > br.total) r = 100;
+                        if (r == 0) st = SS_BUILD;
+                        else { result = r == 100 ? ST_NEED_INPUT : r; st = SS_FINISH; }
+                    } else { result = ST_E_DATA; st = SS_FINISH; }
+                }
+            }
+            st = __shfl_sync(CZK_FULL, st, 0);
+            if (st == SS_FINISH) break;
+            if (st == SS_BLOCK) continue;  // a stored block was taken whole
+            // SS_BUILD: the warp builds both tables
+            nl = __shfl_sync(CZK_FULL, nl, 0);
+            nd = __shfl_sync(CZK_FULL, nd, 0);
+            __syncwarp();
+            int rc = build_one_table(my, my.u.lens, nl, false, lane);
+            if (!rc) rc = build_one_table(my, my.u.lens + nl, nd, true, lane);
+            __syncwarp();
+            if (rc) { if (lane == 0) { result = ST_E_DATA; } st = SS_FINISH; break; }
+            if (lane == 0) {
+                // ---- the symbols of this block
+                st = SS_BLOCK;
+                for (;;) {
+                    if (emit && tp_end - tp < 8) { emit = false; overflow = 1; }
+                    br.refill();
+                    uint32_t e = my.lit_tab[br.peek(CZK_LIT_BITS)];
+                    if ((e & 0xfff0u) == CZK_L_LONG) e = decode_long_lit(my, br.peek(15));
+                    const uint32_t pay = e >> 4;
+                    if (pay < 0x100) {  // literal
+                        br.skip(e & 15);
+                        pos++;
+                        lit |= pay << (8 * nlit);
+                        if (++nlit == 3) { CZKW_PUT(CZK_TOK_LIT | (3u << 24) | lit); lit = 0; nlit = 0; }
+                        // (bits past the end can only have been used once the last word is in the buffer)
+                        if (br.widx >= br.wend && br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
+                        continue;
+                    }
+                    if (!(pay & 0x800)) {
+                        if (pay == 0x100) {  // end of block
+                            br.skip(e & 15);
+                            if (br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
+                            if (bfinal) { result = ST_FINISHED; st = SS_FINISH; }
+                            break;
+                        }
+                        result = br.consumed() + ((e & 15) ? (e & 15) : 1) > br.total ? ST_NEED_INPUT : ST_E_DATA;  // invalid code
+                        st = SS_FINISH;
+                        break;
+                    }
+                    br.skip(e & 15);
+                    const uint32_t eb = (pay >> 8) & 7;
+                    const uint32_t len = 3 + (pay & 0xff) + br.peek(eb);
+                    br.skip(eb);
+                    br.refill();
+                    uint32_t de = my.dist_tab[br.peek(CZK_DIST_BITS)];
+                    if (de & CZK_D_LONG) de = decode_long_dist(my, br.peek(15));
+                    if (de & CZK_D_INVALID) { result = br.consumed() + 1 > br.total ? ST_NEED_INPUT : ST_E_DATA; st = SS_FINISH; break; }
+                    br.skip(de & 15);
+                    const uint32_t deb = (de >> 4) & 15;
+                    const uint32_t dist = (((de >> 8) & 3) << deb) + 1 + br.peek(deb);
+                    br.skip(deb);
+                    if (br.widx >= br.wend && br.overrun()) { result = ST_NEED_INPUT; st = SS_FINISH; break; }
+                    if ((uint64_t)dist > pos && !run_mid) { result = ST_E_DATA; st = SS_FINISH; break; }  // "invalid distance too far back"
+                    CZKW_FLUSH_LIT();
+                    CZKW_PUT(len | (dist << 9));
+                    pos += len;
+                }
+            }
+            st = __shfl_sync(CZK_FULL, st, 0);
+            if (st == SS_FINISH) break;
+        }
+        if (lane == 0) {
+            if (emit && nlit && tp_end - tp < 2) { emit = false; overflow = 1; }
+            CZKW_FLUSH_LIT();
+            TokMeta m;
+            m.ntok = (uint32_t)(tp - tp0);
+            m.status = result;
+            m.out_len = pos;
+            m.expect = 0;
+            m.wrap = 0;
+            Q.meta[unit] = m;
+            RunResult rr;
+            rr.end_bit = br.consumed();
+            rr.final_block = result == ST_FINISHED ? 1u : 0u;
+            rr.tok_overflow = overflow;
+            Q.run_res[unit] = rr;
+        }
+        __syncwarp();
+#undef CZKW_FLUSH_LIT
+#undef CZKW_PUT
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // 3. phase B of a run into 16-bit symbols (the token-parallel resolution of inflate_lz_kernel, on symbols)
 #define CZK_MARK 0x8000u
 

@@ -124,6 +124,11 @@ struct SimRunsBackend {
     }
     bool tok(const TwoPhaseParams &Q) {
         cusim::set_seed(seed++);
+        const char *force = getenv("CUSIM_TOKW");  // "1": always the warp-per-run kernel, "0": never (tests pin both)
+        if (!Q.count_only && (force ? force[0] == '1' : seed % 4 < 2)) {  // (default: half of the launches)
+            cusim::launch(grid, 2 * 32, 0, inflate_tokw_kernel<2>, Q);
+            return true;
+        }
         TwoPhaseParams QL = Q;
         QL.lane_step = seed % 3 == 0 ? 8 : seed % 3 == 1 ? 32 : 0;
         if (Q.count_only) cusim::launch(grid, 2 * 32, inflate_tok_smem_bytes<2>(), inflate_tok_kernel<2, false>, QL);

@@ -85,3 +85,17 @@ def test_sim_runs_dense_tokens_are_emitted_again_with_exact_room(alice):
     outs, ok, lens, cons, nruns = simlib.sim_inflate_runs([s, zcomp(alice * 2, 6, 15)], [len(d), 2 * len(alice)], 15, chunk_bytes=4096, seed=17)
     assert ok[0] and outs[0] == d and cons[0] == len(s)
     assert ok[1] and outs[1] == alice * 2
+
+
+@pytest.mark.parametrize("tokw", ["0", "1"])
+def test_sim_runs_both_phase_a_kernels(alice, tokw, monkeypatch):
+    """Phase A of a run has two kernels — a lane per run (inflate_tok_kernel, also with only every n-th lane taking a run) and a
+    warp per run with one decoding lane and look-up tables (inflate_tokw_kernel, launches with few runs): every case above again
+    with each of them pinned."""
+    monkeypatch.setenv("CUSIM_TOKW", tokw)
+    for wbits in (15, 31, -15):
+        test_sim_runs_zlib_made_streams(alice, wbits)
+    test_sim_runs_find_true_block_starts(alice)
+    test_sim_runs_mixed_blocks_and_auto_sniff(alice)
+    test_sim_runs_decline_what_they_cannot_prove(alice)
+    test_sim_runs_dense_tokens_are_emitted_again_with_exact_room(alice)
