@@ -297,7 +297,8 @@ static int inflate_shard(InflateWork &w, int dev, size_t u0, size_t u1, const ui
                                    (const uint64_t *)(dm + m_outoff) + a, (uint64_t *)(dm + m_lens) + a, (int32_t *)(dm + m_stat) + a,
                                    (uint64_t *)(dm + m_cons) + a, checks ? (uint32_t *)(dm + m_chk) + 2 * a : nullptr, window_bits,
                                    segment_mode, checks ? 3 : 0, big ? wsk + wsk_bytes : wsk, big ? 256 : wsk_bytes, obk - oa,
-                                   d_ids ? d_ids + (big ? n_small[k] : 0) : nullptr, big ? n_big[k] : n_small[k], big);
+                                   d_ids ? d_ids + (big ? n_small[k] : 0) : nullptr, big ? n_big[k] : n_small[k],
+                                   big | (nsub == 1 && !skip ? 2 : 0));
             if (r) return r;
         }
         if (tracing) cudaEventRecord(tr.k, st);

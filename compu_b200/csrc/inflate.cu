@@ -122,7 +122,7 @@ static uint32_t tok_lane_step(const DeviceCtx *ctx, uint64_t n) {
 
 template <int WA, int WB, int H>
 static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateParams &P, void *d_ws, uint64_t ws_bytes,
-                            uint64_t total_out_bytes, size_t n_span) {
+                            uint64_t total_out_bytes, size_t n_span, bool alone = false) {
     if (ws_bytes < inflate_workspace_bytes(n_span, total_out_bytes)) {
         set_error("inflate workspace too small: %llu < %llu (see cz_inflate_workspace_bytes)", (unsigned long long)ws_bytes,
                   (unsigned long long)inflate_workspace_bytes(n_span, total_out_bytes));
@@ -188,9 +188,12 @@ static int launch_two_phase(cudaStream_t st, DeviceCtx *ctx, const czk::InflateP
             if (!CZ_CUDA(cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_l))) return CZ_E_MEM;
             conf_l[d] = true;
         }
-        // (dense lanes here: these launches are the sub-batches of the pipelined host path, several of them in flight at once —
-        //  one unit per warp made cfg2 end to end 136 ms instead of 98 ms; the sparse launch is for the runs of long streams)
-        CZ_KL(kl<<<(unsigned)((P.n + 32 * WL - 1) / (32 * WL)), WL * 32, smem_l, st>>>(Q));
+        // Dense lanes for the sub-batches of the pipelined host path: several of them are in flight at once, and one unit per
+        // warp made cfg2 end to end 136 ms instead of 98 ms. A launch that is the caller's whole (small) batch has the machine to
+        // itself: there only every lane_step-th lane takes a unit, like the runs of a long stream.
+        Q.lane_step = alone ? tok_lane_step(ctx, P.n) : 0;
+        const uint64_t lanes_needed = (uint64_t)P.n * (Q.lane_step ? Q.lane_step : 1);
+        CZ_KL(kl<<<(unsigned)((lanes_needed + 32 * WL - 1) / (32 * WL)), WL * 32, smem_l, st>>>(Q));
     } else
     CZ_KL(ka<<<(unsigned)ga, WA * 32, smem, st>>>(Q));
     if (g_prof_on) cudaEventRecord(pr.e1, st);
@@ -514,6 +517,8 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
                    uint32_t *d_checks, int window_bits, int segment_mode, int check_kind, void *d_ws, uint64_t ws_bytes,
                    uint64_t total_out_bytes, const uint32_t *d_ids, size_t n_ids, int big) {
     if (n == 0 || (d_ids && n_ids == 0)) return 0;
+    const bool alone = (big & 2) != 0;  // bit 1: this launch is the caller's whole batch (nothing else of the call is in flight)
+    big &= 1;
     if (n > 0xfffffff0u) { set_error("too many units in one launch"); return CZ_E_STREAM; }
     if (ws_bytes < 256 || !d_ws) { set_error("inflate workspace too small"); return CZ_E_MEM; }
     if (!(window_bits == -15 || window_bits == 15 || window_bits == 31 || window_bits == 47) && !segment_mode) {
@@ -534,7 +539,7 @@ int launch_inflate(cudaStream_t st, DeviceCtx *ctx, size_t n, const uint8_t *d_i
     if (big) return launch_cfg<1, 8>(st, ctx, P);
     // default configurations
     if (c.D == 1 && c.W == 8) return launch_cfg<1, 8>(st, ctx, P);
-    if (c.D == -2 && (c.W == 14 || c.W == 0)) return launch_two_phase<14, 8, 0>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n);
+    if (c.D == -2 && (c.W == 14 || c.W == 0)) return launch_two_phase<14, 8, 0>(st, ctx, P, d_ws, ws_bytes, total_out_bytes, n, alone);
 #ifdef CZ_EXPERIMENTS
 #define CZ_CFG(d, w) if (c.D == d && c.W == w) return launch_cfg<d, w>(st, ctx, P)
     CZ_CFG(2, 8); CZ_CFG(4, 7); CZ_CFG(4, 4); CZ_CFG(8, 7); CZ_CFG(8, 4); CZ_CFG(8, 2); CZ_CFG(16, 3);
